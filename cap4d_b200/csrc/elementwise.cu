@@ -1,0 +1,304 @@
+// Data-movement and small fp32 kernels around the tensor-core path: input pack (ref-mask mix +
+// im2col of the 4-channel latent + pose conditioning), output mix, up/down-sampling layout
+// transforms, the timestep-embedding MLPs, weight repacking and the fused CFG + DDIM update.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace cap4d {
+
+namespace {
+
+// ---- input pack: mmdm_unet.py:77-95 -----------------------------------------------------------
+// out[(n,y,x)][k]: k < 9*cin   -> tap (ky,kx) = k / cin, channel ci = k % cin of the masked latent
+//                  k < 9*cin+cc -> pos_enc[n,y,x,k-9*cin]
+//                  else 0
+__global__ void input_pack_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                  const float* __restrict__ mask, const float* __restrict__ pos, int n_img, int cin,
+                                  int H, int W, int cc, int kpad, bf16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % kpad);
+    const size_t pix = i / kpad;
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float v = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const size_t sp = static_cast<size_t>(sy) * W + sx;
+        const float m = mask[static_cast<size_t>(n) * H * W + sp];
+        const size_t idx = (static_cast<size_t>(n) * cin + ci) * H * W + sp;
+        // x = z_input * ref_mask + x * logical_not(ref_mask)
+        v = z[idx] * m + x[idx] * (m == 0.f ? 1.f : 0.f);
+      }
+    } else if (k < 9 * cin + cc) {
+      v = pos[pix * cc + (k - 9 * cin)];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// ---- output mix: mmdm_unet.py:77,122-125 ------------------------------------------------------
+__global__ void output_mix_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ x,
+                                  const float* __restrict__ z, const float* __restrict__ mask, int n_img, int cout,
+                                  int H, int W, float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n_img) * cout * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t sp = i % (static_cast<size_t>(H) * W);
+    const int c = static_cast<int>((i / (static_cast<size_t>(H) * W)) % cout);
+    const size_t n = i / (static_cast<size_t>(H) * W * cout);
+    const float m = mask[n * H * W + sp];
+    const float hv = h[(n * H * W + sp) * ldh + c];
+    out[i] = (x[i] - z[i]) * m + hv * (m == 0.f ? 1.f : 0.f);
+  }
+}
+
+// ---- fp32 NHWC -> bf16 NHWC nearest 2x (openaimodel.py:111-117) --------------------------------
+__global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C, bf16* __restrict__ out) {
+  const int quads = C >> 2;
+  const size_t total = static_cast<size_t>(n_img) * H * W * quads;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int qd = static_cast<int>(i % quads);
+    const size_t pix = i / quads;
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const uint2 u = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const int W2 = 2 * W, H2 = 2 * H;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const size_t o = ((n * H2 + (2 * yy + dy)) * W2 + (2 * xx + dx)) * C + qd * 4;
+        *reinterpret_cast<uint2*>(out + o) = u;
+      }
+  }
+}
+
+// ---- fp32 NHWC -> bf16 parity planes for the stride-2 conv (openaimodel.py:150-153) ------------
+__global__ void parity_split_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
+                                    bf16* __restrict__ out) {
+  const int quads = C >> 2;
+  const size_t total = static_cast<size_t>(n_img) * H * W * quads;
+  const int H2 = H >> 1, W2 = W >> 1;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int qd = static_cast<int>(i % quads);
+    const size_t pix = i / quads;
+    const int xx = static_cast<int>(pix % W);
+    const int yy = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const int plane = (yy & 1) * 2 + (xx & 1);
+    const size_t o = (((static_cast<size_t>(plane) * n_img + n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * C + qd * 4;
+    *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ---- timestep embedding: util.py:154-174 -------------------------------------------------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n_img, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * half) return;
+  const int n = i / half, k = i - n * half;
+  // freqs = exp(-ln(10000) * k / half) in fp32, like torch
+  const float f = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+  const float a = static_cast<float>(t[n]) * f;
+  out[static_cast<size_t>(n) * dim + k] = cosf(a);
+  out[static_cast<size_t>(n) * dim + half + k] = sinf(a);
+  if ((dim & 1) && k == 0) out[static_cast<size_t>(n) * dim + dim - 1] = 0.f;
+}
+
+// ---- skinny fp32 linear: out[n][j] = act(sum_k W[j][k] in[n][k] + b[j]), n <= a few dozen -------
+// one warp per output column j; lanes split K; 16 rows of `in` per pass
+__global__ void skinny_linear_kernel(const float* __restrict__ in, int n_rows, int K, const float* __restrict__ Wm,
+                                     const float* __restrict__ bias, int n_out, int silu_out, float* __restrict__ out) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n_out) return;
+  const float* wr = Wm + static_cast<size_t>(j) * K;
+  for (int r0 = 0; r0 < n_rows; r0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if (r0 + r < n_rows) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r0 + r) * K + k));
+          acc[r] += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && r0 + r < n_rows) {
+        v += bias[j];
+        if (silu_out) v = v / (1.0f + expf(-v));
+        out[static_cast<size_t>(r0 + r) * n_out + j] = v;
+      }
+    }
+  }
+}
+
+// ---- weight repacks ---------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW,
+                                        bf16* __restrict__ out, int ldk, int k_offset) {
+  const size_t total = static_cast<size_t>(O) * I * KH * KW;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // destination-major enumeration: (o, tap, i)
+    const int i = static_cast<int>(idx % I);
+    const int tap = static_cast<int>((idx / I) % (KH * KW));
+    const size_t o = idx / (static_cast<size_t>(I) * KH * KW);
+    const float v = w[(o * I + i) * KH * KW + tap];
+    out[o * ldk + k_offset + static_cast<size_t>(tap) * I + i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int cols, bf16* __restrict__ out, int ldk,
+                                   int k_offset, int row_offset) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = idx / cols, c = idx % cols;
+    out[(row_offset + r) * ldk + k_offset + c] = __float2bfloat16(w[idx]);
+  }
+}
+
+// ---- CFG + DDIM update with scatter: cap4d/mmdm/sampler.py:205-231 -----------------------------
+// eps layout: [2*n_groups][V][chw]; batch b < n_groups = unconditional half of group b,
+// b + n_groups = conditional half.  Only views R..V-1 are generated.
+__device__ __forceinline__ float ddim_one(float x, float eu, float ec, float cfg, float x_coef, float e_coef) {
+  const float e = __fadd_rn(eu, __fmul_rn(cfg, __fsub_rn(ec, eu)));
+  return __fadd_rn(__fmul_rn(x, x_coef), __fmul_rn(e, e_coef));
+}
+
+__global__ void cfg_ddim_kernel(float* __restrict__ latents, const float* __restrict__ eps,
+                                const long long* __restrict__ gen_idx, int n_groups, int V, int R, int chw, float cfg,
+                                float x_coef, float e_coef) {
+  const int G = V - R;
+  const int q4 = chw >> 2;
+  const size_t total = static_cast<size_t>(n_groups) * G * q4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i % q4);
+    const int v = static_cast<int>((i / q4) % G);
+    const int g = static_cast<int>(i / (static_cast<size_t>(q4) * G));
+    const float4 eu = __ldg(reinterpret_cast<const float4*>(eps + (static_cast<size_t>(g) * V + R + v) * chw) + e);
+    const float4 ec =
+        __ldg(reinterpret_cast<const float4*>(eps + (static_cast<size_t>(g + n_groups) * V + R + v) * chw) + e);
+    const long long dst = gen_idx[g * G + v];
+    float4* xp = reinterpret_cast<float4*>(latents + static_cast<size_t>(dst) * chw) + e;
+    float4 xv = *xp;
+    // model_output = uncond + cfg * (cond - uncond);  x = x * x_coef + e_t * e_coef
+    // (separately rounded mul/add like the reference's eager ops: no FMA contraction)
+    xv.x = ddim_one(xv.x, eu.x, ec.x, cfg, x_coef, e_coef);
+    xv.y = ddim_one(xv.y, eu.y, ec.y, cfg, x_coef, e_coef);
+    xv.z = ddim_one(xv.z, eu.z, ec.z, cfg, x_coef, e_coef);
+    xv.w = ddim_one(xv.w, eu.w, ec.w, cfg, x_coef, e_coef);
+    *xp = xv;
+  }
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+cudaError_t launch_input_pack(const float* x, const float* z_input, const float* ref_mask, const float* pos_enc,
+                              int n_img, int cin, int H, int W, int ccond, int kpad, bf16* out,
+                              cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  input_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, z_input, ref_mask, pos_enc, n_img, cin, H, W, ccond,
+                                                              kpad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
+                              int n_img, int cout, int H, int W, float* out, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_img) * cout * H * W;
+  output_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, x, z_input, ref_mask, n_img, cout, H, W, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample2x_bf16(const float* x, int n_img, int H, int W, int C, bf16* out, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * (C / 4);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, H, W, C, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, int C, bf16* out,
+                                     cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * (C / 4);
+  parity_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, H, W, C, out);
+  return cudaGetLastError();
+}
+
+size_t time_embed_scratch_bytes(int n_img, int model_ch, int emb_ch) {
+  return static_cast<size_t>(n_img) * (model_ch + 2 * emb_ch) * sizeof(float);
+}
+
+cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int emb_ch, const float* w1,
+                              const float* b1, const float* w2, const float* b2, const float* wall,
+                              const float* ball, int n_all, float* scratch, float* out, cudaStream_t stream) {
+  if (model_ch % 4 != 0 || emb_ch % 4 != 0) {
+    set_error("time_embed: channel counts must be multiples of 4");
+    return cudaErrorInvalidValue;
+  }
+  float* temb = scratch;
+  float* h1 = temb + static_cast<size_t>(n_img) * model_ch;
+  float* se = h1 + static_cast<size_t>(n_img) * emb_ch;
+  const int half = model_ch / 2;
+  timestep_embedding_kernel<<<(n_img * half + 127) / 128, 128, 0, stream>>>(t, n_img, model_ch, temb);
+  const int wpb = 8;
+  // time_embed: Linear -> SiLU -> Linear (openaimodel.py:528-533); every consumer applies SiLU first
+  // (ResBlock.emb_layers, openaimodel.py:203-209), so silu(emb) is what is kept.
+  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(temb, n_img, model_ch, w1, b1, emb_ch, 1, h1);
+  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(h1, n_img, emb_ch, w2, b2, emb_ch, 1, se);
+  skinny_linear_kernel<<<(n_all + wpb - 1) / wpb, wpb * 32, 0, stream>>>(se, n_img, emb_ch, wall, ball, n_all, 0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
+                                    int k_offset, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(O) * I * KH * KW;
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, int ldk, int k_offset, int row_offset,
+                               cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  pack_matrix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, rows, cols, out, ldk, k_offset, row_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long long* gen_idx, int n_groups, int V,
+                                   int R, int chw, float cfg, float x_coef, float e_coef, cudaStream_t stream) {
+  if (chw % 4 != 0) {
+    set_error("cfg_ddim_update: latent size must be a multiple of 4");
+    return cudaErrorInvalidValue;
+  }
+  const size_t total = static_cast<size_t>(n_groups) * (V - R) * (chw / 4);
+  cfg_ddim_kernel<<<grid_for(total, 256), 256, 0, stream>>>(latents, eps, gen_idx, n_groups, V, R, chw, cfg, x_coef,
+                                                            e_coef);
+  return cudaGetLastError();
+}
+
+}  // namespace cap4d

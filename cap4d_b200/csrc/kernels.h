@@ -1,0 +1,154 @@
+// Internal host-side launch API of the cap4d_b200 CUDA kernels (not part of the
+// C ABI; see include/cap4d_b200.h for the exported boundary).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace cap4d {
+
+typedef __nv_bfloat16 bf16;
+
+// Thread-local error text returned by cap4d_b200_last_error().
+void set_error(const std::string& msg);
+const char* get_error();
+
+int sm_count();
+
+// ---------------------------------------------------------------------------
+// Tensor-core GEMM / implicit-GEMM convolution (gemm_tc.cu)
+//   out[M, N] = epilogue( A[M, K] * W[N, K]^T )
+// A is bf16, either a plain row-major matrix or an NHWC activation tensor
+// addressed through a tap table (3x3 conv, stride 1 or the stride-2
+// parity-plane form); an optional second plain A segment appends extra K
+// (fused 1x1 skip convolution).  W is bf16 row-major [N][K_total].
+// ---------------------------------------------------------------------------
+enum GemmOutMode { OUT_F32 = 0, OUT_BF16 = 1, OUT_GEGLU_BF16 = 2 };
+
+struct GemmParams {
+  int M, N;          // logical output size (GEGLU: N counts the interleaved x|gate columns)
+  int BN;            // N tile, multiple of 32, <= 256
+  int tiles_m, tiles_n;
+  int num_kb;        // K / 64 over all segments
+  int seg0_kb;       // k-blocks served by A (taps * cin_kb for conv); the rest come from A2
+  int a_conv;        // 0: A is 2-D [M][K]; 1: A is 4-D NHWC via the tap table
+  int cin_kb;        // conv: k-blocks per tap (Cin / 64)
+  int W, H;          // conv: spatial size of the OUTPUT grid (= box geometry)
+  int box_h, box_n;  // conv: M tile = box_n images x box_h rows x W columns = 128 pixels
+  int n_taps;
+  int tap_dx[9], tap_dy[9], tap_dn[9];  // coordinate offsets per tap (dn: image-index offset, parity planes)
+  int stages;        // smem pipeline depth
+  // epilogue
+  int out_mode;
+  void* out;          // fp32 or bf16, row-major, leading dimension ldo
+  int ldo;
+  const float* bias;     // [N] or null (GEGLU: interleaved like the weights)
+  const float* rowbias;  // [M / rowbias_div][rowbias_ld] or null: per-image additive vector (timestep embedding)
+  int rowbias_div, rowbias_ld;
+  const float* residual;  // fp32 [M][ldr] or null
+  int ldr;
+};
+
+struct GemmPlan {
+  CUtensorMap tmA, tmA2, tmB;
+  GemmParams p;
+  int grid;
+  size_t smem_bytes;
+  double flops;  // 2*M*N*K, for reporting
+};
+
+struct ConvGeom {
+  int n_img, H, W;    // output grid
+  int taps;           // 1 (1x1 / plain) or 9
+  int stride;         // 1 or 2 (2: A holds the 4 parity planes [4][n_img][H][W][C])
+};
+
+// Plain GEMM: A [M][K] bf16 (lda == K), optional second segment A2 [M][K2].
+// Returns false (and sets the error text) on invalid geometry.
+bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2, int K2, const bf16* Wt, int N,
+                    int out_mode, void* out, int ldo, const float* bias, const float* rowbias, int rowbias_div,
+                    int rowbias_ld, const float* residual, int ldr);
+
+// Implicit-GEMM 3x3 convolution, pad 1: A NHWC bf16 [n_img][H_in][W_in][Cin]
+// (stride 2: parity planes, see ConvGeom).  Optional A2 [M][K2] plain segment.
+bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, const bf16* A2, int K2,
+                    const bf16* Wt, int N, int out_mode, void* out, int ldo, const float* bias, const float* rowbias,
+                    int rowbias_div, int rowbias_ld, const float* residual, int ldr);
+
+cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Multi-view flash attention, head_dim 64 (attn_tc.cu)
+//   qkv: bf16 [M][3C] rows = tokens, columns = [q | k | v], head h at h*64
+//   out: bf16 [M][C]
+// Tokens [s*L, (s+1)*L) form sequence s (L = h*w for per-view attention,
+// V*h*w for the cross-view "3d" attention).
+// ---------------------------------------------------------------------------
+struct AttnPlan {
+  CUtensorMap tmQKV;
+  int M, C, L, n_seq, heads;
+  bf16* out;
+  float scale_log2;  // softmax scale * log2(e)
+  dim3 grid;
+  size_t smem_bytes;
+  double flops;  // 4 * n_seq * heads * L * L * 64
+};
+bool make_attn_plan(AttnPlan* plan, const bf16* qkv, bf16* out, int M, int C, int L, float scale);
+cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Norms (norm.cu)
+// ---------------------------------------------------------------------------
+// GroupNorm(32 groups) over NHWC fp32, optionally over the channel
+// concatenation of two tensors (C1 from x1, C2 from x2); writes bf16
+// [M][C1+C2] = (silu?)(gn(x)) and optionally a raw bf16 copy of x.
+// partial: scratch fp32 [n_img][GN_MAX_CHUNKS][32][2].
+enum { GN_MAX_CHUNKS = 64 };
+cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
+                             const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
+                             cudaStream_t stream);
+size_t groupnorm_partial_bytes(int n_img);
+
+// LayerNorm over the last dim of fp32 [M][C] -> bf16 [M][C]
+cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                             bf16* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Elementwise / data-movement (elementwise.cu)
+// ---------------------------------------------------------------------------
+// Input stage (mmdm_unet.py:77-95): ref-mask latent mix, 3x3 im2col of the 4-ch
+// latent and the 50-ch pose conditioning packed into one bf16 row of kpad
+// columns: [9*cin im2col | ccond pos_enc | 0...].
+cudaError_t launch_input_pack(const float* x, const float* z_input, const float* ref_mask, const float* pos_enc,
+                              int n_img, int cin, int H, int W, int ccond, int kpad, bf16* out,
+                              cudaStream_t stream);
+// Output stage (mmdm_unet.py:118-125): eps = x_input*mask + h*(1-mask), NHWC(ld) -> [n_img][cout][H][W]
+cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
+                              int n_img, int cout, int H, int W, float* out, cudaStream_t stream);
+// fp32 NHWC -> bf16 NHWC, nearest 2x upsample
+cudaError_t launch_upsample2x_bf16(const float* x, int n_img, int H, int W, int C, bf16* out, cudaStream_t stream);
+// fp32 NHWC -> bf16 parity planes [4][n_img][H/2][W/2][C] (plane = (y&1)*2 + (x&1))
+cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, int C, bf16* out,
+                                     cudaStream_t stream);
+// timestep embedding + time_embed MLP + all ResBlock emb_layers (fp32):
+//   temb[n] = [cos(t f), sin(t f)] ; e = W2 silu(W1 temb + b1) + b2 ; out[n][:] = Wall silu(e) + ball
+cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int emb_ch, const float* w1,
+                              const float* b1, const float* w2, const float* b2, const float* wall,
+                              const float* ball, int n_all, float* scratch, float* out, cudaStream_t stream);
+size_t time_embed_scratch_bytes(int n_img, int model_ch, int emb_ch);
+// CFG combine + DDIM update (sampler.py:205-231) with scatter:
+//   eps = eu + cfg (ec - eu) over the generated views of each group;
+//   x[idx[g]] = x[idx[g]] * x_coef + eps * e_coef
+// eps: [2*n_groups][V][chw] (uncond halves first, then cond halves), R leading reference views skipped.
+cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long long* gen_idx, int n_groups, int V,
+                                   int R, int chw, float cfg, float x_coef, float e_coef, cudaStream_t stream);
+// fp32 -> bf16 weight repacks (device side)
+cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
+                                    int k_offset, cudaStream_t stream);  // out[o][k_offset + (kh*KW+kw)*I + i]
+cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, int ldk, int k_offset, int row_offset,
+                               cudaStream_t stream);                     // out[row_offset + r][k_offset + c]
+
+}  // namespace cap4d

@@ -1,0 +1,1219 @@
+// MMDM U-Net executor: topology, weight repacking, static launch plan.
+//
+// Mirrors MMDMUnetModel (cap4d/mmdm/net/mmdm_unet.py:14-126) on top of UNetModel's block topology
+// (controlnet/ldm/modules/diffusionmodules/openaimodel.py:544-774) and SpatioTemporalTransformer
+// (cap4d/mmdm/net/attention.py:330-387).  Activations are NHWC (token-major) fp32 on the residual
+// stream and bf16 as MMA operands; a forward is a fixed list of kernel launches on one stream with
+// every intermediate carved out of a caller-provided workspace (no allocation after planning).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cap4d_b200.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace cap4d {
+
+// ---------------------------------------------------------------------------------------------
+// error text
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+
+#define CUDA_OK(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+      return false;                                                                        \
+    }                                                                                      \
+  } while (0)
+
+namespace {
+
+enum OpClass { CLS_CONV = 0, CLS_LINEAR = 1, CLS_ATTN = 2, CLS_GN = 3, CLS_LN = 4, CLS_OTHER = 5 };
+
+struct Op {
+  int cls;
+  int launches;
+  double flops;
+  double bytes;
+  std::function<cudaError_t(cudaStream_t)> run;
+};
+
+struct RawTensor {
+  float* d = nullptr;
+  size_t numel = 0;
+  std::vector<int64_t> shape;
+};
+
+// small device kernels used only at weight-pack time
+__global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b != nullptr ? b[i] : 0.f);
+}
+// GEGLU interleave (attention.py:68-75): rows [0,inner) = x, [inner,2*inner) = gate ->
+// packed row (r/32)*64 + half*32 + r%32
+__global__ void pack_geglu_kernel(const float* w, const float* b, int inner, int K, bf16* wout, float* bout) {
+  const size_t total = static_cast<size_t>(2) * inner * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / K, c = i % K;
+    const int half = row >= static_cast<size_t>(inner);
+    const size_t r = row - static_cast<size_t>(half) * inner;
+    const size_t prow = (r / 32) * 64 + half * 32 + (r % 32);
+    wout[prow * K + c] = __float2bfloat16(w[i]);
+    if (c == 0) bout[prow] = b[row];
+  }
+}
+
+// first-fit offset allocator over the workspace; identical decisions in the sizing and the real pass
+struct Arena {
+  std::map<size_t, size_t> free_;  // offset -> size
+  size_t top = 0, peak = 0;
+  static size_t align(size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); }
+  size_t alloc(size_t bytes) {
+    bytes = align(bytes ? bytes : 1);
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        size_t off = it->first, rem = it->second - bytes;
+        free_.erase(it);
+        if (rem) free_[off + bytes] = rem;
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    peak = std::max(peak, top);
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = align(bytes ? bytes : 1);
+    auto it = free_.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != free_.end() && it->first + it->second == nx->first) {
+      it->second += nx->second;
+      free_.erase(nx);
+    }
+    if (it != free_.begin()) {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) {
+        pv->second += it->second;
+        free_.erase(it);
+        it = pv;
+      }
+    }
+    if (it->first + it->second == top) {
+      top = it->first;
+      free_.erase(it);
+    }
+  }
+};
+
+struct Buf {  // a workspace tensor
+  size_t off = 0, bytes = 0;
+  int M = 0, C = 0;
+  bool valid = false;
+};
+
+struct ResW {
+  std::string prefix;
+  int cin = 0, cout = 0;
+  bool skip = false;
+  float *gn1_g = nullptr, *gn1_b = nullptr, *gn2_g = nullptr, *gn2_b = nullptr;
+  bf16 *w1 = nullptr, *w2 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr;
+  int emb_off = 0;
+};
+struct TfW {
+  std::string prefix;
+  int C = 0;
+  bool is3d = false;
+  float *gn_g = nullptr, *gn_b = nullptr, *ln1_g = nullptr, *ln1_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr;
+  bf16 *wpi = nullptr, *wqkv = nullptr, *wo = nullptr, *wff1 = nullptr, *wff2 = nullptr, *wpo = nullptr;
+  float *bpi = nullptr, *bo = nullptr, *bff1 = nullptr, *bff2 = nullptr, *bpo = nullptr;
+};
+struct ConvW {
+  std::string prefix;
+  int cin = 0, cout = 0;
+  bf16* w = nullptr;
+  float* b = nullptr;
+};
+
+enum LayerKind { L_RES, L_TF, L_DOWN, L_UP };
+struct Layer {
+  LayerKind kind;
+  int idx;
+};
+typedef std::vector<Layer> Block;
+
+struct IoPtrs {
+  const float *x = nullptr, *z = nullptr, *mask = nullptr, *pos = nullptr;
+  const long long* t = nullptr;
+  float* out = nullptr;
+};
+
+struct Unet {
+  cap4d_b200_unet_config cfg;
+  int emb_ch = 0, kpad_in = 0, n_all = 0;
+  std::vector<ResW> res;
+  std::vector<TfW> tf;
+  std::vector<ConvW> down, up;
+  std::vector<Block> input_blocks, output_blocks;  // input_blocks[0] is conv_in (handled separately)
+  Block middle;
+  std::vector<int> input_block_chans;
+  std::map<std::string, RawTensor> raw;
+  std::vector<void*> owned;  // packed device buffers
+  bool finalized = false;
+  // packed globals
+  bf16* w_in = nullptr;
+  float* b_in = nullptr;
+  float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *wall = nullptr, *ball = nullptr;
+  float *out_gn_g = nullptr, *out_gn_b = nullptr;
+  bf16* w_out = nullptr;
+  float* b_out = nullptr;
+  // plan
+  std::vector<Op> ops;
+  IoPtrs io;
+  int pB = 0, pV = 0, pH = 0, pW = 0;
+  void* p_ws = nullptr;
+  size_t p_ws_bytes = 0;
+  std::vector<cudaEvent_t> events;
+
+  ~Unet() {
+    for (void* p : owned) cudaFree(p);
+    for (auto& kv : raw)
+      if (kv.second.d) cudaFree(kv.second.d);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+  }
+
+  // ------------------------------------------------------------------ topology
+  bool attn_at(int ds) const {
+    for (int i = 0; i < cfg.n_attention_resolutions; ++i)
+      if (cfg.attention_resolutions[i] == ds) return true;
+    return false;
+  }
+
+  int add_res(const std::string& prefix, int cin, int cout) {
+    ResW r;
+    r.prefix = prefix;
+    r.cin = cin;
+    r.cout = cout;
+    r.skip = cin != cout;
+    r.emb_off = n_all;
+    n_all += cout;
+    res.push_back(r);
+    return static_cast<int>(res.size()) - 1;
+  }
+  int add_tf(const std::string& prefix, int C, int mult) {
+    TfW t;
+    t.prefix = prefix;
+    t.C = C;
+    t.is3d = mult >= 2;  // mmdm_unet.py:49-55
+    tf.push_back(t);
+    return static_cast<int>(tf.size()) - 1;
+  }
+
+  bool build_topology() {
+    const int mc = cfg.model_channels;
+    emb_ch = 4 * mc;
+    kpad_in = ((9 * cfg.in_channels + cfg.condition_channels + 63) / 64) * 64;
+    if (cfg.num_head_channels != 64) {
+      set_error("only num_head_channels == 64 is implemented");
+      return false;
+    }
+    if (cfg.n_levels < 1 || cfg.n_levels > CAP4D_B200_MAX_LEVELS || mc % 64 != 0) {
+      set_error("model_channels must be a multiple of 64 and 1 <= n_levels <= 8");
+      return false;
+    }
+    char buf[128];
+    input_blocks.clear();
+    input_blocks.push_back(Block());  // conv_in
+    input_block_chans.assign(1, mc);
+    int ch = mc, ds = 1;
+    for (int level = 0; level < cfg.n_levels; ++level) {
+      const int mult = cfg.channel_mult[level];
+      for (int nr = 0; nr < cfg.num_res_blocks; ++nr) {
+        Block b;
+        snprintf(buf, sizeof(buf), "input_blocks.%d.", static_cast<int>(input_blocks.size()));
+        b.push_back({L_RES, add_res(std::string(buf) + "0.", ch, mult * mc)});
+        ch = mult * mc;
+        if (attn_at(ds)) b.push_back({L_TF, add_tf(std::string(buf) + "1.", ch, mult)});
+        input_blocks.push_back(b);
+        input_block_chans.push_back(ch);
+      }
+      if (level != cfg.n_levels - 1) {
+        Block b;
+        snprintf(buf, sizeof(buf), "input_blocks.%d.0.op.", static_cast<int>(input_blocks.size()));
+        ConvW d;
+        d.prefix = buf;
+        d.cin = d.cout = ch;
+        down.push_back(d);
+        b.push_back({L_DOWN, static_cast<int>(down.size()) - 1});
+        input_blocks.push_back(b);
+        input_block_chans.push_back(ch);
+        ds *= 2;
+      }
+    }
+    middle.clear();
+    middle.push_back({L_RES, add_res("middle_block.0.", ch, ch)});
+    middle.push_back({L_TF, add_tf("middle_block.1.", ch, cfg.channel_mult[cfg.n_levels - 1])});
+    middle.push_back({L_RES, add_res("middle_block.2.", ch, ch)});
+    output_blocks.clear();
+    std::vector<int> chans = input_block_chans;
+    for (int level = cfg.n_levels - 1; level >= 0; --level) {
+      const int mult = cfg.channel_mult[level];
+      for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+        const int ich = chans.back();
+        chans.pop_back();
+        Block b;
+        snprintf(buf, sizeof(buf), "output_blocks.%d.", static_cast<int>(output_blocks.size()));
+        b.push_back({L_RES, add_res(std::string(buf) + "0.", ch + ich, mc * mult)});
+        ch = mc * mult;
+        int sub = 1;
+        if (attn_at(ds)) {
+          b.push_back({L_TF, add_tf(std::string(buf) + "1.", ch, mult)});
+          sub = 2;
+        }
+        if (level && i == cfg.num_res_blocks) {
+          ConvW u;
+          u.prefix = std::string(buf) + std::to_string(sub) + ".conv.";
+          u.cin = u.cout = ch;
+          up.push_back(u);
+          b.push_back({L_UP, static_cast<int>(up.size()) - 1});
+          ds /= 2;
+        }
+        output_blocks.push_back(b);
+      }
+    }
+    if (ch != mc) {
+      set_error("topology: final channel count != model_channels");
+      return false;
+    }
+    return true;
+  }
+
+  // ------------------------------------------------------------------ weights
+  template <typename T>
+  T* dev_alloc(size_t n, bool zero = false) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 16));
+    owned.push_back(p);
+    return static_cast<T*>(p);
+  }
+
+  bool get(const std::string& name, size_t numel, const RawTensor** out) {
+    auto it = raw.find(name);
+    if (it == raw.end()) {
+      set_error("missing weight: " + name);
+      return false;
+    }
+    if (it->second.numel != numel) {
+      set_error("weight " + name + ": expected " + std::to_string(numel) + " elements, got " +
+                std::to_string(it->second.numel));
+      return false;
+    }
+    *out = &it->second;
+    return true;
+  }
+  // fp32 parameter used as is (kept alive in `raw`)
+  bool fp(const std::string& name, size_t numel, float** out) {
+    const RawTensor* t;
+    if (!get(name, numel, &t)) return false;
+    *out = t->d;
+    return true;
+  }
+  bool pack_linear(const std::string& name, int rows, int cols, bf16** out) {
+    const RawTensor* t;
+    if (!get(name, static_cast<size_t>(rows) * cols, &t)) return false;
+    *out = dev_alloc<bf16>(static_cast<size_t>(rows) * cols);
+    if (!*out) {
+      set_error("cudaMalloc failed for " + name);
+      return false;
+    }
+    CUDA_OK(launch_pack_matrix(t->d, rows, cols, *out, cols, 0, 0, 0));
+    consumed.push_back(name);
+    return true;
+  }
+  std::vector<std::string> consumed;
+
+  bool finalize() {
+    if (finalized) return true;
+    const int mc = cfg.model_channels;
+    const RawTensor* t;
+    // ---- conv_in + cond_linear fused into one [mc][kpad] matrix (mmdm_unet.py:92-107)
+    {
+      w_in = dev_alloc<bf16>(static_cast<size_t>(mc) * kpad_in, true);
+      b_in = dev_alloc<float>(mc);
+      if (!get("input_blocks.0.0.weight", static_cast<size_t>(mc) * cfg.in_channels * 9, &t)) return false;
+      CUDA_OK(launch_pack_conv_weight(t->d, mc, cfg.in_channels, 3, 3, w_in, kpad_in, 0, 0));
+      consumed.push_back("input_blocks.0.0.weight");
+      if (!get("cond_linear.weight", static_cast<size_t>(mc) * cfg.condition_channels, &t)) return false;
+      CUDA_OK(launch_pack_matrix(t->d, mc, cfg.condition_channels, w_in, kpad_in, 9 * cfg.in_channels, 0, 0));
+      consumed.push_back("cond_linear.weight");
+      float *b0, *b1;
+      if (!fp("input_blocks.0.0.bias", mc, &b0) || !fp("cond_linear.bias", mc, &b1)) return false;
+      vec_add_kernel<<<(mc + 255) / 256, 256>>>(b0, b1, b_in, mc);
+    }
+    // ---- time embedding (fp32)
+    if (!fp("time_embed.0.weight", static_cast<size_t>(emb_ch) * mc, &te_w1) || !fp("time_embed.0.bias", emb_ch, &te_b1) ||
+        !fp("time_embed.2.weight", static_cast<size_t>(emb_ch) * emb_ch, &te_w2) ||
+        !fp("time_embed.2.bias", emb_ch, &te_b2))
+      return false;
+    wall = dev_alloc<float>(static_cast<size_t>(n_all) * emb_ch);
+    ball = dev_alloc<float>(n_all);
+    if (!wall || !ball) {
+      set_error("cudaMalloc failed (emb layers)");
+      return false;
+    }
+    // ---- ResBlocks
+    for (ResW& r : res) {
+      const std::string& p = r.prefix;
+      if (!fp(p + "in_layers.0.weight", r.cin, &r.gn1_g) || !fp(p + "in_layers.0.bias", r.cin, &r.gn1_b) ||
+          !fp(p + "out_layers.0.weight", r.cout, &r.gn2_g) || !fp(p + "out_layers.0.bias", r.cout, &r.gn2_b) ||
+          !fp(p + "in_layers.2.bias", r.cout, &r.b1))
+        return false;
+      if (!get(p + "in_layers.2.weight", static_cast<size_t>(r.cout) * r.cin * 9, &t)) return false;
+      r.w1 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * 9 * r.cin);
+      if (!r.w1) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cin, 3, 3, r.w1, 9 * r.cin, 0, 0));
+      consumed.push_back(p + "in_layers.2.weight");
+      const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
+      if (!get(p + "out_layers.3.weight", static_cast<size_t>(r.cout) * r.cout * 9, &t)) return false;
+      r.w2 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * k2);
+      r.b2 = dev_alloc<float>(r.cout);
+      if (!r.w2 || !r.b2) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cout, 3, 3, r.w2, k2, 0, 0));
+      consumed.push_back(p + "out_layers.3.weight");
+      float *bo, *bs = nullptr;
+      if (!fp(p + "out_layers.3.bias", r.cout, &bo)) return false;
+      if (r.skip) {
+        // 1x1 skip conv (openaimodel.py:235-242) appended along K of the second 3x3 conv
+        if (!get(p + "skip_connection.weight", static_cast<size_t>(r.cout) * r.cin, &t)) return false;
+        CUDA_OK(launch_pack_matrix(t->d, r.cout, r.cin, r.w2, k2, 9 * r.cout, 0, 0));
+        consumed.push_back(p + "skip_connection.weight");
+        if (!fp(p + "skip_connection.bias", r.cout, &bs)) return false;
+      }
+      vec_add_kernel<<<(r.cout + 255) / 256, 256>>>(bo, bs, r.b2, r.cout);
+      // emb_layers (openaimodel.py:203-209) -> rows of the shared [n_all][emb_ch] matrix
+      if (!get(p + "emb_layers.1.weight", static_cast<size_t>(r.cout) * emb_ch, &t)) return false;
+      CUDA_OK(cudaMemcpy(wall + static_cast<size_t>(r.emb_off) * emb_ch, t->d, t->numel * sizeof(float),
+                         cudaMemcpyDeviceToDevice));
+      consumed.push_back(p + "emb_layers.1.weight");
+      if (!get(p + "emb_layers.1.bias", r.cout, &t)) return false;
+      CUDA_OK(cudaMemcpy(ball + r.emb_off, t->d, t->numel * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    // ---- transformers
+    for (TfW& w : tf) {
+      const std::string& p = w.prefix;
+      const std::string tb = p + "transformer_blocks.0.";
+      const int C = w.C;
+      if (!fp(p + "norm.weight", C, &w.gn_g) || !fp(p + "norm.bias", C, &w.gn_b) ||
+          !fp(p + "proj_in.bias", C, &w.bpi) || !fp(p + "proj_out.bias", C, &w.bpo) ||
+          !fp(tb + "norm1.weight", C, &w.ln1_g) || !fp(tb + "norm1.bias", C, &w.ln1_b) ||
+          !fp(tb + "norm3.weight", C, &w.ln3_g) || !fp(tb + "norm3.bias", C, &w.ln3_b) ||
+          !fp(tb + "attn1.to_out.0.bias", C, &w.bo) || !fp(tb + "ff.net.2.bias", C, &w.bff2))
+        return false;
+      if (!pack_linear(p + "proj_in.weight", C, C, &w.wpi) || !pack_linear(p + "proj_out.weight", C, C, &w.wpo) ||
+          !pack_linear(tb + "attn1.to_out.0.weight", C, C, &w.wo) ||
+          !pack_linear(tb + "ff.net.2.weight", C, 4 * C, &w.wff2))
+        return false;
+      // fused QKV [3C][C] (attention.py:168-170, no bias)
+      w.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
+      if (!w.wqkv) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      const char* names[3] = {"attn1.to_q.weight", "attn1.to_k.weight", "attn1.to_v.weight"};
+      for (int i = 0; i < 3; ++i) {
+        if (!get(tb + names[i], static_cast<size_t>(C) * C, &t)) return false;
+        CUDA_OK(launch_pack_matrix(t->d, C, C, w.wqkv, C, 0, i * C, 0));
+        consumed.push_back(tb + names[i]);
+      }
+      // GEGLU projection [8C][C] interleaved
+      const RawTensor* tbias;
+      if (!get(tb + "ff.net.0.proj.weight", static_cast<size_t>(8) * C * C, &t) ||
+          !get(tb + "ff.net.0.proj.bias", static_cast<size_t>(8) * C, &tbias))
+        return false;
+      w.wff1 = dev_alloc<bf16>(static_cast<size_t>(8) * C * C);
+      w.bff1 = dev_alloc<float>(static_cast<size_t>(8) * C);
+      if (!w.wff1 || !w.bff1) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      pack_geglu_kernel<<<sm_count() * 8, 256>>>(t->d, tbias->d, 4 * C, C, w.wff1, w.bff1);
+      consumed.push_back(tb + "ff.net.0.proj.weight");
+    }
+    // ---- down / up convs
+    for (int pass = 0; pass < 2; ++pass) {
+      for (ConvW& c : (pass == 0 ? down : up)) {
+        if (!get(c.prefix + "weight", static_cast<size_t>(c.cout) * c.cin * 9, &t)) return false;
+        c.w = dev_alloc<bf16>(static_cast<size_t>(c.cout) * 9 * c.cin);
+        if (!c.w) {
+          set_error("cudaMalloc failed");
+          return false;
+        }
+        CUDA_OK(launch_pack_conv_weight(t->d, c.cout, c.cin, 3, 3, c.w, 9 * c.cin, 0, 0));
+        consumed.push_back(c.prefix + "weight");
+        if (!fp(c.prefix + "bias", c.cout, &c.b)) return false;
+      }
+    }
+    // ---- out: GN -> SiLU -> conv3x3 mc -> out_channels, N padded to 32 (openaimodel.py:770-774)
+    {
+      if (!fp("out.0.weight", mc, &out_gn_g) || !fp("out.0.bias", mc, &out_gn_b)) return false;
+      if (cfg.out_channels > 32) {
+        set_error("out_channels > 32 is not implemented");
+        return false;
+      }
+      w_out = dev_alloc<bf16>(static_cast<size_t>(32) * 9 * mc, true);
+      b_out = dev_alloc<float>(32, true);
+      if (!get("out.2.weight", static_cast<size_t>(cfg.out_channels) * mc * 9, &t)) return false;
+      CUDA_OK(launch_pack_conv_weight(t->d, cfg.out_channels, mc, 3, 3, w_out, 9 * mc, 0, 0));
+      consumed.push_back("out.2.weight");
+      if (!get("out.2.bias", cfg.out_channels, &t)) return false;
+      CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+    // the big fp32 originals are no longer needed
+    for (const std::string& name : consumed) {
+      auto it = raw.find(name);
+      if (it != raw.end() && it->second.d) {
+        cudaFree(it->second.d);
+        raw.erase(it);
+      }
+    }
+    consumed.clear();
+    finalized = true;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ planning
+  struct PlanCtx {
+    Arena arena;
+    bool dry = true;
+    uint8_t* base = nullptr;
+    int n_img = 0, V = 0;
+    float* emb_all = nullptr;
+    float* gn_partial = nullptr;
+    std::vector<Op>* ops = nullptr;
+    template <typename T>
+    T* ptr(const Buf& b) const {
+      return reinterpret_cast<T*>(base + b.off);
+    }
+    Buf alloc(int M, int C, size_t elem) {
+      Buf b;
+      b.M = M;
+      b.C = C;
+      b.bytes = static_cast<size_t>(M) * C * elem;
+      b.off = arena.alloc(b.bytes);
+      b.valid = true;
+      return b;
+    }
+    void release(Buf& b) {
+      if (b.valid) arena.release(b.off, b.bytes);
+      b.valid = false;
+    }
+  };
+
+  bool add_gemm_op(PlanCtx& c, int cls, const GemmPlan& plan) {
+    Op op;
+    op.cls = cls;
+    op.launches = 1;
+    op.flops = plan.flops;
+    op.bytes = 0;
+    GemmPlan copy = plan;
+    op.run = [copy](cudaStream_t s) { return launch_gemm(copy, s); };
+    c.ops->push_back(op);
+    return true;
+  }
+
+  bool op_gn(PlanCtx& c, const Buf& x1, const Buf* x2, int hw, const float* g, const float* b, float eps, int silu,
+             const Buf& out, const Buf* raw_out) {
+    if (c.dry) return true;
+    const float* p1 = c.ptr<float>(x1);
+    const float* p2 = x2 ? c.ptr<float>(*x2) : nullptr;
+    const int C1 = x1.C, C2 = x2 ? x2->C : 0;
+    bf16* po = c.ptr<bf16>(out);
+    bf16* pr = raw_out ? c.ptr<bf16>(*raw_out) : nullptr;
+    float* partial = c.gn_partial;
+    const int n_img = c.n_img;
+    Op op;
+    op.cls = CLS_GN;
+    op.launches = 2;
+    op.flops = 0;
+    op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
+    op.run = [=](cudaStream_t s) {
+      return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s);
+    };
+    c.ops->push_back(op);
+    return true;
+  }
+
+  bool op_ln(PlanCtx& c, const Buf& x, const float* g, const float* b, const Buf& out) {
+    if (c.dry) return true;
+    const float* px = c.ptr<float>(x);
+    bf16* po = c.ptr<bf16>(out);
+    const int M = x.M, C = x.C;
+    Op op;
+    op.cls = CLS_LN;
+    op.launches = 1;
+    op.flops = 0;
+    op.bytes = static_cast<double>(M) * C * 6;
+    op.run = [=](cudaStream_t s) { return launch_layernorm(px, M, C, g, b, 1e-5f, po, s); };
+    c.ops->push_back(op);
+    return true;
+  }
+
+  // ResBlock._forward (openaimodel.py:256-276); x2 != null: input is cat([x1, x2], channels)
+  bool plan_res(PlanCtx& c, const ResW& r, const Buf& x1, const Buf* x2, int H, int W, Buf* out) {
+    const int M = x1.M, hw = H * W;
+    const int cin = x1.C + (x2 ? x2->C : 0);
+    if (cin != r.cin) {
+      set_error("plan: channel mismatch at " + r.prefix);
+      return false;
+    }
+    Buf a1 = c.alloc(M, cin, 2), xb;
+    if (r.skip) xb = c.alloc(M, cin, 2);
+    if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr)) return false;
+    Buf h = c.alloc(M, r.cout, 4);
+    ConvGeom g{c.n_img, H, W, 9, 1};
+    if (!c.dry) {
+      GemmPlan p;
+      if (!make_conv_plan(&p, c.ptr<bf16>(a1), g, cin, nullptr, 0, r.w1, r.cout, OUT_F32, c.ptr<float>(h), r.cout,
+                          r.b1, c.emb_all + r.emb_off, hw, n_all, nullptr, 0))
+        return false;
+      add_gemm_op(c, CLS_CONV, p);
+    }
+    c.release(a1);
+    Buf a2 = c.alloc(M, r.cout, 2);
+    if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr)) return false;
+    c.release(h);
+    *out = c.alloc(M, r.cout, 4);
+    if (!c.dry) {
+      GemmPlan p;
+      const float* residual = r.skip ? nullptr : c.ptr<float>(x1);
+      if (!make_conv_plan(&p, c.ptr<bf16>(a2), g, r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? cin : 0, r.w2,
+                          r.cout, OUT_F32, c.ptr<float>(*out), r.cout, r.b2, nullptr, 1, 0, residual, r.cout))
+        return false;
+      add_gemm_op(c, CLS_CONV, p);
+    }
+    c.release(a2);
+    c.release(xb);
+    return true;
+  }
+
+  // SpatioTemporalTransformer.forward (attention.py:375-387) + BasicTransformerBlock (:311-326)
+  bool plan_tf(PlanCtx& c, const TfW& w, const Buf& x, int H, int W, Buf* out) {
+    const int M = x.M, C = w.C, hw = H * W;
+    Buf a = c.alloc(M, C, 2);
+    if (!op_gn(c, x, nullptr, hw, w.gn_g, w.gn_b, 1e-6f, 0, a, nullptr)) return false;
+    Buf t0 = c.alloc(M, C, 4);
+    auto gemm = [&](const Buf& A, int K, const bf16* Wt, int N, int mode, const Buf& o, int ldo, const float* bias,
+                    const float* residual) -> bool {
+      if (c.dry) return true;
+      GemmPlan p;
+      if (!make_gemm_plan(&p, c.ptr<bf16>(A), M, K, nullptr, 0, Wt, N, mode, c.base + o.off, ldo, bias, nullptr, 1, 0,
+                          residual, C))
+        return false;
+      return add_gemm_op(c, CLS_LINEAR, p);
+    };
+    if (!gemm(a, C, w.wpi, C, OUT_F32, t0, C, w.bpi, nullptr)) return false;
+    c.release(a);
+    Buf n1 = c.alloc(M, C, 2);
+    if (!op_ln(c, t0, w.ln1_g, w.ln1_b, n1)) return false;
+    Buf qkv = c.alloc(M, 3 * C, 2);
+    if (!gemm(n1, C, w.wqkv, 3 * C, OUT_BF16, qkv, 3 * C, nullptr, nullptr)) return false;
+    c.release(n1);
+    Buf o = c.alloc(M, C, 2);
+    if (!c.dry) {
+      AttnPlan ap;
+      const int L = w.is3d ? c.V * hw : hw;  // attention.py:233 vs :237
+      if (!make_attn_plan(&ap, c.ptr<bf16>(qkv), c.ptr<bf16>(o), M, C, L, 0.125f)) return false;
+      Op op;
+      op.cls = CLS_ATTN;
+      op.launches = 1;
+      op.flops = ap.flops;
+      op.bytes = 0;
+      op.run = [ap](cudaStream_t s) { return launch_attn(ap, s); };
+      c.ops->push_back(op);
+    }
+    c.release(qkv);
+    Buf t1 = c.alloc(M, C, 4);
+    if (!gemm(o, C, w.wo, C, OUT_F32, t1, C, w.bo, c.dry ? nullptr : c.ptr<float>(t0))) return false;
+    c.release(o);
+    c.release(t0);
+    Buf n3 = c.alloc(M, C, 2);
+    if (!op_ln(c, t1, w.ln3_g, w.ln3_b, n3)) return false;
+    Buf gg = c.alloc(M, 4 * C, 2);
+    if (!gemm(n3, C, w.wff1, 8 * C, OUT_GEGLU_BF16, gg, 4 * C, w.bff1, nullptr)) return false;
+    c.release(n3);
+    Buf t2 = c.alloc(M, C, 2);
+    if (!gemm(gg, 4 * C, w.wff2, C, OUT_BF16, t2, C, w.bff2, c.dry ? nullptr : c.ptr<float>(t1))) return false;
+    c.release(gg);
+    c.release(t1);
+    *out = c.alloc(M, C, 4);
+    if (!gemm(t2, C, w.wpo, C, OUT_F32, *out, C, w.bpo, c.dry ? nullptr : c.ptr<float>(x))) return false;
+    c.release(t2);
+    return true;
+  }
+
+  // Downsample (openaimodel.py:135-161): conv3x3 stride 2
+  bool plan_down(PlanCtx& c, const ConvW& w, const Buf& x, int H, int W, Buf* out) {
+    const int C = w.cin;
+    Buf pp = c.alloc(x.M, C, 2);
+    *out = c.alloc(x.M / 4, w.cout, 4);
+    if (!c.dry) {
+      const float* px = c.ptr<float>(x);
+      bf16* ppp = c.ptr<bf16>(pp);
+      const int n_img = c.n_img;
+      Op op;
+      op.cls = CLS_OTHER;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(x.M) * C * 6;
+      op.run = [=](cudaStream_t s) { return launch_parity_split_bf16(px, n_img, H, W, C, ppp, s); };
+      c.ops->push_back(op);
+      GemmPlan p;
+      ConvGeom g{c.n_img, H / 2, W / 2, 9, 2};
+      if (!make_conv_plan(&p, ppp, g, C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1,
+                          0, nullptr, 0))
+        return false;
+      add_gemm_op(c, CLS_CONV, p);
+    }
+    c.release(pp);
+    return true;
+  }
+
+  // Upsample (openaimodel.py:92-120): nearest 2x, conv3x3
+  bool plan_up(PlanCtx& c, const ConvW& w, const Buf& x, int H, int W, Buf* out) {
+    const int C = w.cin;
+    Buf upb = c.alloc(x.M * 4, C, 2);
+    *out = c.alloc(x.M * 4, w.cout, 4);
+    if (!c.dry) {
+      const float* px = c.ptr<float>(x);
+      bf16* pu = c.ptr<bf16>(upb);
+      const int n_img = c.n_img;
+      Op op;
+      op.cls = CLS_OTHER;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(x.M) * C * (4 + 8);
+      op.run = [=](cudaStream_t s) { return launch_upsample2x_bf16(px, n_img, H, W, C, pu, s); };
+      c.ops->push_back(op);
+      GemmPlan p;
+      ConvGeom g{c.n_img, 2 * H, 2 * W, 9, 1};
+      if (!make_conv_plan(&p, pu, g, C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1,
+                          0, nullptr, 0))
+        return false;
+      add_gemm_op(c, CLS_CONV, p);
+    }
+    c.release(upb);
+    return true;
+  }
+
+  bool plan_block(PlanCtx& c, const Block& blk, Buf x, const Buf* skip, int* H, int* W, Buf* out) {
+    // x is owned by this call (released once consumed); skip is owned by the caller
+    Buf cur = x;
+    for (size_t li = 0; li < blk.size(); ++li) {
+      const Layer& l = blk[li];
+      Buf nxt;
+      switch (l.kind) {
+        case L_RES:
+          if (!plan_res(c, res[l.idx], cur, (li == 0) ? skip : nullptr, *H, *W, &nxt)) return false;
+          break;
+        case L_TF:
+          if (!plan_tf(c, tf[l.idx], cur, *H, *W, &nxt)) return false;
+          break;
+        case L_DOWN:
+          if (!plan_down(c, down[l.idx], cur, *H, *W, &nxt)) return false;
+          *H /= 2;
+          *W /= 2;
+          break;
+        case L_UP:
+          if (!plan_up(c, up[l.idx], cur, *H, *W, &nxt)) return false;
+          *H *= 2;
+          *W *= 2;
+          break;
+      }
+      c.release(cur);
+      cur = nxt;
+    }
+    *out = cur;
+    return true;
+  }
+
+  bool build_plan(PlanCtx& c, int B, int V, int H, int W) {
+    const int mc = cfg.model_channels;
+    const int n_img = B * V;
+    c.n_img = n_img;
+    c.V = V;
+    const int down_factor = 1 << (cfg.n_levels - 1);
+    if (H % down_factor != 0 || W % down_factor != 0) {
+      set_error("H and W must be divisible by 2^(n_levels-1)");
+      return false;
+    }
+    // persistent small buffers
+    Buf emb = c.alloc(n_img, n_all, 4);
+    Buf te_scratch;
+    te_scratch.bytes = time_embed_scratch_bytes(n_img, mc, emb_ch);
+    te_scratch.off = c.arena.alloc(te_scratch.bytes);
+    te_scratch.valid = true;
+    Buf gnp;
+    gnp.bytes = groupnorm_partial_bytes(n_img);
+    gnp.off = c.arena.alloc(gnp.bytes);
+    gnp.valid = true;
+    if (!c.dry) {
+      c.emb_all = c.ptr<float>(emb);
+      c.gn_partial = c.ptr<float>(gnp);
+    }
+    const int M0 = n_img * H * W;
+    // ---- input stage
+    Buf a0 = c.alloc(M0, kpad_in, 2);
+    Buf h = c.alloc(M0, mc, 4);
+    if (!c.dry) {
+      IoPtrs* iop = &io;
+      bf16* pa0 = c.ptr<bf16>(a0);
+      const int cin = cfg.in_channels, cc = cfg.condition_channels, kp = kpad_in;
+      {
+        Op op;
+        op.cls = CLS_OTHER;
+        op.launches = 1;
+        op.flops = 0;
+        op.bytes = static_cast<double>(M0) * (kp * 2 + cc * 4 + cin * 8);
+        op.run = [=](cudaStream_t s) {
+          return launch_input_pack(iop->x, iop->z, iop->mask, iop->pos, n_img, cin, H, W, cc, kp, pa0, s);
+        };
+        c.ops->push_back(op);
+      }
+      {
+        float* scratch = c.ptr<float>(te_scratch);
+        float* embp = c.emb_all;
+        const int nall = n_all, ech = emb_ch;
+        const float *w1 = te_w1, *b1 = te_b1, *w2 = te_w2, *b2 = te_b2, *wa = wall, *ba = ball;
+        Op op;
+        op.cls = CLS_OTHER;
+        op.launches = 4;
+        op.flops = 2.0 * n_img * (static_cast<double>(mc) * ech + static_cast<double>(ech) * ech +
+                                  static_cast<double>(ech) * nall);
+        op.bytes = 4.0 * (static_cast<double>(mc) * ech + static_cast<double>(ech) * ech + static_cast<double>(ech) * nall);
+        op.run = [=](cudaStream_t s) {
+          return launch_time_embed(iop->t, n_img, mc, ech, w1, b1, w2, b2, wa, ba, nall, scratch, embp, s);
+        };
+        c.ops->push_back(op);
+      }
+      GemmPlan p;
+      if (!make_gemm_plan(&p, pa0, M0, kp, nullptr, 0, w_in, mc, OUT_F32, c.ptr<float>(h), mc, b_in, nullptr, 1, 0,
+                          nullptr, 0))
+        return false;
+      add_gemm_op(c, CLS_LINEAR, p);
+    }
+    c.release(a0);
+    // ---- down path
+    std::vector<Buf> hs;
+    hs.push_back(h);
+    int curH = H, curW = W;
+    Buf cur = h;
+    for (size_t bi = 1; bi < input_blocks.size(); ++bi) {
+      Buf nxt;
+      // the block input is also a skip tensor: do not let plan_block release it
+      Buf keep = cur;
+      keep.valid = false;
+      if (!plan_block(c, input_blocks[bi], keep, nullptr, &curH, &curW, &nxt)) return false;
+      hs.push_back(nxt);
+      cur = nxt;
+    }
+    // ---- middle
+    {
+      Buf keep = cur;
+      keep.valid = false;
+      Buf nxt;
+      if (!plan_block(c, middle, keep, nullptr, &curH, &curW, &nxt)) return false;
+      cur = nxt;  // owned
+    }
+    // ---- up path
+    for (size_t bi = 0; bi < output_blocks.size(); ++bi) {
+      Buf skip = hs.back();
+      hs.pop_back();
+      Buf nxt;
+      if (!plan_block(c, output_blocks[bi], cur, &skip, &curH, &curW, &nxt)) return false;
+      c.release(skip);
+      cur = nxt;
+    }
+    // ---- out
+    Buf a = c.alloc(M0, mc, 2);
+    if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr)) return false;
+    c.release(cur);
+    Buf o32 = c.alloc(M0, 32, 4);
+    if (!c.dry) {
+      GemmPlan p;
+      ConvGeom g{n_img, H, W, 9, 1};
+      if (!make_conv_plan(&p, c.ptr<bf16>(a), g, mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
+                          nullptr, 1, 0, nullptr, 0))
+        return false;
+      add_gemm_op(c, CLS_CONV, p);
+      IoPtrs* iop = &io;
+      const float* po = c.ptr<float>(o32);
+      const int cout = cfg.out_channels;
+      Op op;
+      op.cls = CLS_OTHER;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(M0) * cout * 16;
+      op.run = [=](cudaStream_t s) {
+        return launch_output_mix(po, 32, iop->x, iop->z, iop->mask, n_img, cout, H, W, iop->out, s);
+      };
+      c.ops->push_back(op);
+    }
+    c.release(a);
+    c.release(o32);
+    return true;
+  }
+
+  bool workspace_bytes(int B, int V, int H, int W, size_t* bytes) {
+    PlanCtx c;
+    c.dry = true;
+    std::vector<Op> dummy;
+    c.ops = &dummy;
+    if (!build_plan(c, B, V, H, W)) return false;
+    *bytes = c.arena.peak + 1024;
+    return true;
+  }
+
+  bool ensure_plan(int B, int V, int H, int W, void* ws, size_t ws_bytes) {
+    if (!finalized) {
+      set_error("cap4d_b200_unet_finalize has not been called");
+      return false;
+    }
+    if (B == pB && V == pV && H == pH && W == pW && ws == p_ws && ws_bytes == p_ws_bytes && !ops.empty()) return true;
+    size_t need = 0;
+    if (!workspace_bytes(B, V, H, W, &need)) return false;
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("workspace too small: need " + std::to_string(need) + " bytes");
+      return false;
+    }
+    ops.clear();
+    PlanCtx c;
+    c.dry = false;
+    c.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+    c.ops = &ops;
+    if (!build_plan(c, B, V, H, W)) {
+      ops.clear();
+      return false;
+    }
+    pB = B;
+    pV = V;
+    pH = H;
+    pW = W;
+    p_ws = ws;
+    p_ws_bytes = ws_bytes;
+    return true;
+  }
+
+  bool forward(const IoPtrs& ptrs, int B, int V, int H, int W, void* ws, size_t ws_bytes, cudaStream_t stream,
+               float* class_ms) {
+    if (!ensure_plan(B, V, H, W, ws, ws_bytes)) return false;
+    io = ptrs;
+    if (class_ms == nullptr) {
+      for (size_t i = 0; i < ops.size(); ++i) {
+        cudaError_t e = ops[i].run(stream);
+        if (e != cudaSuccess) {
+          set_error("launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e) + " / " + get_error());
+          return false;
+        }
+      }
+      return true;
+    }
+    while (events.size() < ops.size() + 1) {
+      cudaEvent_t ev;
+      CUDA_OK(cudaEventCreate(&ev));
+      events.push_back(ev);
+    }
+    CUDA_OK(cudaEventRecord(events[0], stream));
+    for (size_t i = 0; i < ops.size(); ++i) {
+      cudaError_t e = ops[i].run(stream);
+      if (e != cudaSuccess) {
+        set_error("launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e));
+        return false;
+      }
+      CUDA_OK(cudaEventRecord(events[i + 1], stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) class_ms[k] = 0.f;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, events[i], events[i + 1]));
+      class_ms[ops[i].cls] += ms;
+    }
+    return true;
+  }
+};
+
+}  // namespace
+}  // namespace cap4d
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace cap4d;
+
+// timing helper for the single-kernel entry points
+template <typename F>
+static int run_timed(F&& launch, cudaStream_t s, float* ms_out, int iters) {
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms_out != nullptr) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t e = launch(s);  // warm-up
+    if (e != cudaSuccess) {
+      set_error(std::string("launch failed: ") + cudaGetErrorString(e) + " / " + get_error());
+      return 8;
+    }
+    cudaEventRecord(e0, s);
+  }
+  for (int i = 0; i < iters; ++i) {
+    cudaError_t e = launch(s);
+    if (e != cudaSuccess) {
+      set_error(std::string("launch failed: ") + cudaGetErrorString(e) + " / " + get_error());
+      return 8;
+    }
+  }
+  if (ms_out != nullptr) {
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      set_error(std::string("kernel failed: ") + cudaGetErrorString(e));
+      return 9;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return 0;
+}
+
+extern "C" {
+
+const char* cap4d_b200_last_error(void) { return get_error(); }
+const char* cap4d_b200_version(void) { return "cap4d_b200 0.1 (sm_100a)"; }
+
+int cap4d_b200_unet_create(const cap4d_b200_unet_config* cfg, void** handle) {
+  if (cfg == nullptr || handle == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  Unet* u = new Unet();
+  u->cfg = *cfg;
+  if (!u->build_topology()) {
+    delete u;
+    return 2;
+  }
+  *handle = u;
+  return 0;
+}
+
+int cap4d_b200_unet_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || name == nullptr || data == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  if (u->finalized) {
+    set_error("weights are already finalized");
+    return 1;
+  }
+  RawTensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    t.numel *= static_cast<size_t>(shape[i]);
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&t.d), std::max<size_t>(t.numel * sizeof(float), 16)) != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed for ") + name);
+    return 3;
+  }
+  cudaError_t e = cudaMemcpy(t.d, data, t.numel * sizeof(float), cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaFree(t.d);
+    set_error(std::string("cudaMemcpy failed for ") + name + ": " + cudaGetErrorString(e));
+    return 3;
+  }
+  auto it = u->raw.find(name);
+  if (it != u->raw.end() && it->second.d) cudaFree(it->second.d);
+  u->raw[name] = t;
+  return 0;
+}
+
+int cap4d_b200_unet_finalize(void* handle) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  return u->finalize() ? 0 : 4;
+}
+
+int cap4d_b200_unet_workspace_bytes(void* handle, int B, int V, int H, int W, size_t* bytes) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || bytes == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  return u->workspace_bytes(B, V, H, W, bytes) ? 0 : 5;
+}
+
+static int forward_impl(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
+                        const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H, int W,
+                        void* workspace, size_t workspace_bytes, void* stream, float* class_ms) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || x == nullptr || timesteps == nullptr || z_input == nullptr || ref_mask == nullptr ||
+      pos_enc == nullptr || out == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  IoPtrs io;
+  io.x = x;
+  io.t = reinterpret_cast<const long long*>(timesteps);
+  io.z = z_input;
+  io.mask = ref_mask;
+  io.pos = pos_enc;
+  io.out = out;
+  return u->forward(io, B, V, H, W, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), class_ms) ? 0 : 6;
+}
+
+int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
+                            const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H, int W,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(handle, x, timesteps, z_input, ref_mask, pos_enc, out, B, V, H, W, workspace, workspace_bytes,
+                      stream, nullptr);
+}
+
+int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
+                                  const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H,
+                                  int W, void* workspace, size_t workspace_bytes, void* stream, float* class_ms) {
+  if (class_ms == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  return forward_impl(handle, x, timesteps, z_input, ref_mask, pos_enc, out, B, V, H, W, workspace, workspace_bytes,
+                      stream, class_ms);
+}
+
+int cap4d_b200_unet_num_launches(void* handle, int* n) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  int total = 0;
+  for (const Op& op : u->ops) total += op.launches;
+  *n = total;
+  return 0;
+}
+
+int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int* launches) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) {
+    if (flops) flops[k] = 0;
+    if (bytes) bytes[k] = 0;
+    if (launches) launches[k] = 0;
+  }
+  for (const Op& op : u->ops) {
+    if (flops) flops[op.cls] += op.flops;
+    if (bytes) bytes[op.cls] += op.bytes;
+    if (launches) launches[op.cls] += op.launches;
+  }
+  return 0;
+}
+
+int cap4d_b200_unet_destroy(void* handle) {
+  delete static_cast<Unet*>(handle);
+  return 0;
+}
+
+int cap4d_b200_cfg_ddim_update(float* latents, const float* eps, const int64_t* gen_idx, int n_groups, int V, int R,
+                               int chw, float cfg_scale, float x_coef, float e_coef, void* stream) {
+  cudaError_t e = launch_cfg_ddim_update(latents, eps, reinterpret_cast<const long long*>(gen_idx), n_groups, V, R, chw,
+                                         cfg_scale, x_coef, e_coef, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    if (e != cudaErrorInvalidValue) set_error(cudaGetErrorString(e));
+    return 7;
+  }
+  return 0;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------
+int cap4d_b200_gemm_bf16(const uint16_t* A, const uint16_t* Wt, int M, int N, int K, const float* bias,
+                         const float* residual, void* out, int out_mode, void* stream, float* ms_out, int iters) {
+  GemmPlan p;
+  const int ldo = (out_mode == OUT_GEGLU_BF16) ? N / 2 : N;
+  if (!make_gemm_plan(&p, reinterpret_cast<const bf16*>(A), M, K, nullptr, 0, reinterpret_cast<const bf16*>(Wt), N,
+                      out_mode, out, ldo, bias, nullptr, 1, 0, residual, ldo))
+    return 10;
+  return run_timed([&](cudaStream_t s) { return launch_gemm(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+int cap4d_b200_conv3x3_bf16(const uint16_t* A, const uint16_t* Wt, int n_img, int H_out, int W_out, int Cin, int Cout,
+                            int stride, const float* bias, const float* rowbias, const float* residual, float* out,
+                            void* stream, float* ms_out, int iters) {
+  GemmPlan p;
+  ConvGeom g{n_img, H_out, W_out, 9, stride};
+  if (!make_conv_plan(&p, reinterpret_cast<const bf16*>(A), g, Cin, nullptr, 0, reinterpret_cast<const bf16*>(Wt), Cout,
+                      OUT_F32, out, Cout, bias, rowbias, H_out * W_out, Cout, residual, Cout))
+    return 10;
+  return run_timed([&](cudaStream_t s) { return launch_gemm(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,
+                              float* ms_out, int iters) {
+  AttnPlan p;
+  if (!make_attn_plan(&p, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), M, C, L, scale)) return 10;
+  return run_timed([&](cudaStream_t s) { return launch_attn(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
+                              const float* gamma, const float* beta, float eps, int apply_silu, uint16_t* out,
+                              uint16_t* raw_out, void* stream, float* ms_out, int iters) {
+  float* partial = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&partial), groupnorm_partial_bytes(n_img)) != cudaSuccess) {
+    set_error("cudaMalloc failed");
+    return 3;
+  }
+  int rc = run_timed(
+      [&](cudaStream_t s) {
+        return launch_groupnorm(x1, C1, x2, C2, n_img, hw, gamma, beta, eps, apply_silu, reinterpret_cast<bf16*>(out),
+                                reinterpret_cast<bf16*>(raw_out), partial, s);
+      },
+      static_cast<cudaStream_t>(stream), ms_out, iters);
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(partial);
+  return rc;
+}
+
+int cap4d_b200_layernorm_bf16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                              uint16_t* out, void* stream, float* ms_out, int iters) {
+  return run_timed(
+      [&](cudaStream_t s) { return launch_layernorm(x, M, C, gamma, beta, eps, reinterpret_cast<bf16*>(out), s); },
+      static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+}  // extern "C"

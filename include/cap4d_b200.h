@@ -1,0 +1,126 @@
+/*
+ * cap4d_b200 -- C ABI of the B200-native MMDM multi-view denoising hot path.
+ *
+ * The reference (hitminxuanwang/cap4d) is pure Python and offers no FFI; its seam for this path
+ * is three duck-typed Python call conventions.  Each entry point below names the reference
+ * interface it replaces.  A Python binding (ctypes, cap4d_b200/_lib.py) is what a maintainer of
+ * the reference would add; see INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a non-zero status otherwise
+ * (cap4d_b200_last_error() returns the text for the calling thread); nothing throws across the
+ * boundary.  All tensor pointers are DEVICE pointers unless stated otherwise, fp32, contiguous,
+ * in the reference's own layouts.  Calls are stream-ordered on `stream` (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream) and never synchronise the device, except
+ * load_weight/finalize.  A handle is not re-entrant; use one handle per thread/stream.
+ */
+#ifndef CAP4D_B200_H_
+#define CAP4D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAP4D_B200_MAX_LEVELS 8
+
+/* Hyper-parameters of MMDMUnetModel (cap4d/mmdm/net/mmdm_unet.py:15-33 +
+ * controlnet/ldm/modules/diffusionmodules/openaimodel.py:448-477), i.e. the `unet_config.params`
+ * block of configs/mmdm/cap4d_mmdm_final.yaml:95-115.  Fixed by the MMDM and therefore not
+ * configurable: use_spatial_transformer=True, transformer_depth=1, conv_resample=True,
+ * resblock_updown=False, use_scale_shift_norm=False, temporal_mode="3d", use_context=False. */
+typedef struct cap4d_b200_unet_config {
+  int in_channels;       /* 4  */
+  int out_channels;      /* 4  */
+  int model_channels;    /* 320 */
+  int condition_channels;/* 50 */
+  int num_res_blocks;    /* 2  */
+  int n_levels;          /* len(channel_mult) = 4 */
+  int channel_mult[CAP4D_B200_MAX_LEVELS];          /* 1,2,4,4 */
+  int n_attention_resolutions;                      /* 3 */
+  int attention_resolutions[CAP4D_B200_MAX_LEVELS]; /* 4,2,1 */
+  int num_head_channels; /* 64 (only 64 is implemented) */
+  int time_steps;        /* V: views per group the "3d" attention spans (8) */
+} cap4d_b200_unet_config;
+
+/* ---- U-Net handle: replaces MMDMUnetModel (mmdm_unet.py:14-126) ------------------------------ */
+
+/* MMDMUnetModel.__init__ (mmdm_unet.py:15-33): derive the block topology from the config. */
+int cap4d_b200_unet_create(const cap4d_b200_unet_config* cfg, void** handle);
+
+/* nn.Module.load_state_dict as used by cap4d/inference/utils.py:44-61: one call per entry of
+ * `model.model.diffusion_model.state_dict()`; `name` is the reference key
+ * (e.g. "input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight"), `data` fp32 on host or device. */
+int cap4d_b200_unet_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim);
+
+/* Repack all weights for the tensor-core kernels (bf16, K-major, fused QKV / GEGLU / skip-conv
+ * layouts).  Fails if any parameter of the topology was not loaded. */
+int cap4d_b200_unet_finalize(void* handle);
+
+/* Scratch needed by one forward at this shape (caller owns the buffer; >= 1024 B aligned). */
+int cap4d_b200_unet_workspace_bytes(void* handle, int B, int V, int H, int W, size_t* bytes);
+
+/* MMDMUnetModel.forward(x, timesteps, context=None, control) (mmdm_unet.py:67-126), reached from
+ * MMLDM.apply_model (cap4d/mmdm/mmdm.py:113-124):
+ *   x, z_input, out: [B][V][C][H][W]   ref_mask: [B][V][1][H][W]   pos_enc: [B][V][H][W][Cc]
+ *   timesteps: int64 [B][V]. */
+int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
+                            const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H, int W,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Instrumentation (no reference counterpart): kernels launched per forward, algorithmic FLOPs per
+ * forward by class, and a forward with CUDA-event timing per kernel class.
+ * classes: 0 conv3x3 (tcgen05 implicit GEMM), 1 linear (tcgen05 GEMM), 2 attention core,
+ *          3 GroupNorm, 4 LayerNorm, 5 other (pack / mix / resample / embedding). */
+#define CAP4D_B200_N_CLASSES 6
+int cap4d_b200_unet_num_launches(void* handle, int* n);
+int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int* launches);
+int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
+                                  const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H,
+                                  int W, void* workspace, size_t workspace_bytes, void* stream, float* class_ms);
+
+int cap4d_b200_unet_destroy(void* handle);
+
+/* ---- sampler update: replaces cap4d/mmdm/sampler.py:205-208 + 215-231 ----------------------
+ * eps: [2*n_groups][V][chw] as returned by the U-Net for the batch
+ * [uncond group 0..n-1 | cond group 0..n-1]; for every group g and generated view v >= R:
+ *   e = eps_u + cfg * (eps_c - eps_u);  latents[gen_idx[g][v-R]] = latents[..] * x_coef + e * e_coef */
+int cap4d_b200_cfg_ddim_update(float* latents, const float* eps, const int64_t* gen_idx, int n_groups, int V, int R,
+                               int chw, float cfg_scale, float x_coef, float e_coef, void* stream);
+
+/* ---- single-kernel entry points (building blocks; used by tests and micro-benchmarks) --------
+ * bf16 tensors are passed as uint16_t*. */
+
+/* torch.nn.functional.linear / 1x1 conv: out[M][N] = A[M][K] W[N][K]^T (+bias[N]) (+residual[M][N]);
+ * out_mode 0: fp32, 1: bf16, 2: GEGLU (attention.py:68-75; W/bias rows interleaved [x32|gate32]). */
+int cap4d_b200_gemm_bf16(const uint16_t* A, const uint16_t* Wt, int M, int N, int K, const float* bias,
+                         const float* residual, void* out, int out_mode, void* stream, float* ms_out, int iters);
+
+/* nn.Conv2d(k=3, pad=1, stride 1|2) on NHWC bf16 (stride 2: parity planes); weights [Cout][9*Cin]
+ * tap-major; optional rowbias[n_img][Cout] (ResBlock emb_out, openaimodel.py:265-274). */
+int cap4d_b200_conv3x3_bf16(const uint16_t* A, const uint16_t* Wt, int n_img, int H_out, int W_out, int Cin, int Cout,
+                            int stride, const float* bias, const float* rowbias, const float* residual, float* out,
+                            void* stream, float* ms_out, int iters);
+
+/* legacy_attention (attention.py:112-132) for head_dim 64 on the fused qkv matrix [M][3C];
+ * sequences are L consecutive rows. */
+int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,
+                              float* ms_out, int iters);
+
+/* GroupNorm32(32, C1+C2)(cat([x1, x2], channel)) (+SiLU) on NHWC fp32 -> bf16; x2 may be NULL. */
+int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
+                              const float* gamma, const float* beta, float eps, int apply_silu, uint16_t* out,
+                              uint16_t* raw_out, void* stream, float* ms_out, int iters);
+
+/* LayerNorm32(C) on fp32 [M][C] -> bf16. */
+int cap4d_b200_layernorm_bf16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                              uint16_t* out, void* stream, float* ms_out, int iters);
+
+const char* cap4d_b200_last_error(void);
+const char* cap4d_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAP4D_B200_H_ */
