@@ -35,6 +35,8 @@ class UnetConfig(ctypes.Structure):
 SIGNATURES = {
     "cap4d_b200_unet_create": (c_int, [POINTER(UnetConfig), POINTER(c_void_p)]),
     "cap4d_b200_unet_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    "cap4d_b200_unet_num_params": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "cap4d_b200_unet_finalize": (c_int, [c_void_p]),
     "cap4d_b200_unet_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "cap4d_b200_unet_forward": (
@@ -49,6 +51,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
          c_size_t, c_void_p, POINTER(c_float)],
     ),
+    "cap4d_b200_unet_collect_timings": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
     "cap4d_b200_unet_destroy": (c_int, [c_void_p]),
     "cap4d_b200_cfg_ddim_update": (
         c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),

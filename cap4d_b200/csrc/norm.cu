@@ -56,13 +56,11 @@ __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const fl
 // grid (n_chunks, n_img), block (TX, TY)
 __global__ void gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw,
                                 int nqi, int cpg, int rows_per_chunk, float* __restrict__ partial) {
-  extern __shared__ float s_ch[];  // [2][C]
+  extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
   const int C = C1 + C2;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  const int tid = ty * TX + tx, nthreads = TX * TY;
-  for (int i = tid; i < 2 * C; i += nthreads) s_ch[i] = 0.f;
-  __syncthreads();
+  const int tid = ty * TX + tx;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
   float sum[GN_MAX_QI][4], sq[GN_MAX_QI][4];
@@ -83,23 +81,24 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, const float* __res
       }
     }
   }
+  float* my = s_ch + static_cast<size_t>(ty) * 2 * C;
 #pragma unroll
   for (int qi = 0; qi < GN_MAX_QI; ++qi) {
     if (qi < nqi) {
       const int c = (tx + qi * TX) * 4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        atomicAdd(&s_ch[c + k], sum[qi][k]);
-        atomicAdd(&s_ch[C + c + k], sq[qi][k]);
-      }
+      *reinterpret_cast<float4*>(my + c) = make_float4(sum[qi][0], sum[qi][1], sum[qi][2], sum[qi][3]);
+      *reinterpret_cast<float4*>(my + C + c) = make_float4(sq[qi][0], sq[qi][1], sq[qi][2], sq[qi][3]);
     }
   }
   __syncthreads();
   if (tid < GN_GROUPS) {
     float s = 0.f, q = 0.f;
-    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-      s += s_ch[c];
-      q += s_ch[C + c];
+    for (int y = 0; y < TY; ++y) {
+      const float* src = s_ch + static_cast<size_t>(y) * 2 * C;
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        s += src[c];
+        q += src[C + c];
+      }
     }
     float* dst = partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + chunk) * GN_GROUPS + tid) * 2;
     dst[0] = s;
@@ -246,12 +245,12 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
     return cudaErrorInvalidValue;
   }
   GnGeom g = gn_geometry(C1, C2, hw);
-  if (g.nqi > GN_MAX_QI) {
+  if (g.nqi > GN_MAX_QI || static_cast<size_t>(2) * C * g.TY * sizeof(float) > 48 * 1024) {
     set_error("groupnorm: too many channels for this kernel");
     return cudaErrorInvalidValue;
   }
   dim3 grid(g.n_chunks, n_img), block(g.TX, g.TY);
-  gn_stats_kernel<<<grid, block, 2 * C * sizeof(float), stream>>>(x1, x2, C1, C2, hw, g.nqi, g.cpg,
+  gn_stats_kernel<<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(x1, x2, C1, C2, hw, g.nqi, g.cpg,
                                                                   g.rows_per_chunk, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

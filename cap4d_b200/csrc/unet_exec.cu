@@ -185,12 +185,17 @@ struct Unet {
   void* p_ws = nullptr;
   size_t p_ws_bytes = 0;
   std::vector<cudaEvent_t> events;
+  std::vector<std::vector<cudaEvent_t>> deferred, event_pool;
 
   ~Unet() {
     for (void* p : owned) cudaFree(p);
     for (auto& kv : raw)
       if (kv.second.d) cudaFree(kv.second.d);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
+    for (auto& v : deferred)
+      for (cudaEvent_t e : v) cudaEventDestroy(e);
+    for (auto& v : event_pool)
+      for (cudaEvent_t e : v) cudaEventDestroy(e);
   }
 
   // ------------------------------------------------------------------ topology
@@ -297,6 +302,73 @@ struct Unet {
       return false;
     }
     return true;
+  }
+
+  // ------------------------------------------------------------------ parameter census
+  // every state_dict entry of MMDMUnetModel for this topology, in a fixed order
+  std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params() const {
+    std::vector<std::pair<std::string, std::vector<int64_t>>> v;
+    const int64_t mc = cfg.model_channels, e = emb_ch;
+    auto add = [&](const std::string& n, std::vector<int64_t> shp) { v.emplace_back(n, std::move(shp)); };
+    add("time_embed.0.weight", {e, mc});
+    add("time_embed.0.bias", {e});
+    add("time_embed.2.weight", {e, e});
+    add("time_embed.2.bias", {e});
+    add("input_blocks.0.0.weight", {mc, cfg.in_channels, 3, 3});
+    add("input_blocks.0.0.bias", {mc});
+    for (const ResW& r : res) {
+      const std::string& p = r.prefix;
+      add(p + "in_layers.0.weight", {r.cin});
+      add(p + "in_layers.0.bias", {r.cin});
+      add(p + "in_layers.2.weight", {r.cout, r.cin, 3, 3});
+      add(p + "in_layers.2.bias", {r.cout});
+      add(p + "emb_layers.1.weight", {r.cout, e});
+      add(p + "emb_layers.1.bias", {r.cout});
+      add(p + "out_layers.0.weight", {r.cout});
+      add(p + "out_layers.0.bias", {r.cout});
+      add(p + "out_layers.3.weight", {r.cout, r.cout, 3, 3});
+      add(p + "out_layers.3.bias", {r.cout});
+      if (r.skip) {
+        add(p + "skip_connection.weight", {r.cout, r.cin, 1, 1});
+        add(p + "skip_connection.bias", {r.cout});
+      }
+    }
+    for (const TfW& w : tf) {
+      const std::string& p = w.prefix;
+      const std::string tb = p + "transformer_blocks.0.";
+      const int64_t C = w.C;
+      add(p + "norm.weight", {C});
+      add(p + "norm.bias", {C});
+      add(p + "proj_in.weight", {C, C});
+      add(p + "proj_in.bias", {C});
+      add(tb + "attn1.to_q.weight", {C, C});
+      add(tb + "attn1.to_k.weight", {C, C});
+      add(tb + "attn1.to_v.weight", {C, C});
+      add(tb + "attn1.to_out.0.weight", {C, C});
+      add(tb + "attn1.to_out.0.bias", {C});
+      add(tb + "norm1.weight", {C});
+      add(tb + "norm1.bias", {C});
+      add(tb + "norm3.weight", {C});
+      add(tb + "norm3.bias", {C});
+      add(tb + "ff.net.0.proj.weight", {8 * C, C});
+      add(tb + "ff.net.0.proj.bias", {8 * C});
+      add(tb + "ff.net.2.weight", {C, 4 * C});
+      add(tb + "ff.net.2.bias", {C});
+      add(p + "proj_out.weight", {C, C});
+      add(p + "proj_out.bias", {C});
+    }
+    for (int pass = 0; pass < 2; ++pass)
+      for (const ConvW& c : (pass == 0 ? down : up)) {
+        add(c.prefix + "weight", {c.cout, c.cin, 3, 3});
+        add(c.prefix + "bias", {c.cout});
+      }
+    add("out.0.weight", {mc});
+    add("out.0.bias", {mc});
+    add("out.2.weight", {cfg.out_channels, mc, 3, 3});
+    add("out.2.bias", {cfg.out_channels});
+    add("cond_linear.weight", {mc, cfg.condition_channels});
+    add("cond_linear.bias", {mc});
+    return v;
   }
 
   // ------------------------------------------------------------------ weights
@@ -922,41 +994,68 @@ struct Unet {
     return true;
   }
 
+  // timed == 0: plain; 1: events around every op, synchronise and return per-class ms;
+  // 2: events recorded but NOT synchronised (collected later by collect_timings)
   bool forward(const IoPtrs& ptrs, int B, int V, int H, int W, void* ws, size_t ws_bytes, cudaStream_t stream,
-               float* class_ms) {
+               int timed, float* class_ms) {
     if (!ensure_plan(B, V, H, W, ws, ws_bytes)) return false;
     io = ptrs;
-    if (class_ms == nullptr) {
-      for (size_t i = 0; i < ops.size(); ++i) {
-        cudaError_t e = ops[i].run(stream);
-        if (e != cudaSuccess) {
-          set_error("launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e) + " / " + get_error());
-          return false;
-        }
+    std::vector<cudaEvent_t>* evs = nullptr;
+    if (timed == 1) {
+      evs = &events;
+    } else if (timed == 2) {
+      if (!event_pool.empty()) {
+        deferred.push_back(std::move(event_pool.back()));
+        event_pool.pop_back();
+      } else {
+        deferred.emplace_back();
       }
-      return true;
+      evs = &deferred.back();
     }
-    while (events.size() < ops.size() + 1) {
-      cudaEvent_t ev;
-      CUDA_OK(cudaEventCreate(&ev));
-      events.push_back(ev);
+    if (evs != nullptr) {
+      while (evs->size() < ops.size() + 1) {
+        cudaEvent_t ev;
+        CUDA_OK(cudaEventCreate(&ev));
+        evs->push_back(ev);
+      }
+      CUDA_OK(cudaEventRecord((*evs)[0], stream));
     }
-    CUDA_OK(cudaEventRecord(events[0], stream));
     for (size_t i = 0; i < ops.size(); ++i) {
       cudaError_t e = ops[i].run(stream);
       if (e != cudaSuccess) {
-        set_error("launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e));
+        set_error("launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e) + " / " + get_error());
         return false;
       }
-      CUDA_OK(cudaEventRecord(events[i + 1], stream));
+      if (evs != nullptr) CUDA_OK(cudaEventRecord((*evs)[i + 1], stream));
     }
-    CUDA_OK(cudaStreamSynchronize(stream));
-    for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) class_ms[k] = 0.f;
+    if (timed == 1) {
+      CUDA_OK(cudaStreamSynchronize(stream));
+      for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) class_ms[k] = 0.f;
+      if (!accumulate(events, class_ms)) return false;
+    }
+    return true;
+  }
+
+  bool accumulate(const std::vector<cudaEvent_t>& evs, float* class_ms) {
     for (size_t i = 0; i < ops.size(); ++i) {
       float ms = 0.f;
-      CUDA_OK(cudaEventElapsedTime(&ms, events[i], events[i + 1]));
+      CUDA_OK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
       class_ms[ops[i].cls] += ms;
     }
+    return true;
+  }
+
+  bool collect_timings(float* class_ms, int* n_runs) {
+    for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) class_ms[k] = 0.f;
+    *n_runs = 0;
+    for (auto& evs : deferred) {
+      if (evs.size() < ops.size() + 1) continue;
+      CUDA_OK(cudaEventSynchronize(evs[ops.size()]));
+      if (!accumulate(evs, class_ms)) return false;
+      ++*n_runs;
+    }
+    for (auto& evs : deferred) event_pool.push_back(std::move(evs));
+    deferred.clear();
     return true;
   }
 };
@@ -1079,7 +1178,7 @@ int cap4d_b200_unet_workspace_bytes(void* handle, int B, int V, int H, int W, si
 
 static int forward_impl(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
                         const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H, int W,
-                        void* workspace, size_t workspace_bytes, void* stream, float* class_ms) {
+                        void* workspace, size_t workspace_bytes, void* stream, int timed, float* class_ms) {
   Unet* u = static_cast<Unet*>(handle);
   if (u == nullptr || x == nullptr || timesteps == nullptr || z_input == nullptr || ref_mask == nullptr ||
       pos_enc == nullptr || out == nullptr) {
@@ -1093,25 +1192,32 @@ static int forward_impl(void* handle, const float* x, const int64_t* timesteps, 
   io.mask = ref_mask;
   io.pos = pos_enc;
   io.out = out;
-  return u->forward(io, B, V, H, W, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), class_ms) ? 0 : 6;
+  return u->forward(io, B, V, H, W, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), timed, class_ms)
+             ? 0
+             : 6;
 }
 
 int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
                             const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H, int W,
                             void* workspace, size_t workspace_bytes, void* stream) {
   return forward_impl(handle, x, timesteps, z_input, ref_mask, pos_enc, out, B, V, H, W, workspace, workspace_bytes,
-                      stream, nullptr);
+                      stream, 0, nullptr);
 }
 
 int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
                                   const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H,
                                   int W, void* workspace, size_t workspace_bytes, void* stream, float* class_ms) {
-  if (class_ms == nullptr) {
+  return forward_impl(handle, x, timesteps, z_input, ref_mask, pos_enc, out, B, V, H, W, workspace, workspace_bytes,
+                      stream, class_ms != nullptr ? 1 : 2, class_ms);
+}
+
+int cap4d_b200_unet_collect_timings(void* handle, float* class_ms, int* n_runs) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || class_ms == nullptr || n_runs == nullptr) {
     set_error("null argument");
     return 1;
   }
-  return forward_impl(handle, x, timesteps, z_input, ref_mask, pos_enc, out, B, V, H, W, workspace, workspace_bytes,
-                      stream, class_ms);
+  return u->collect_timings(class_ms, n_runs) ? 0 : 6;
 }
 
 int cap4d_b200_unet_num_launches(void* handle, int* n) {
@@ -1142,6 +1248,37 @@ int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int*
     if (bytes) bytes[op.cls] += op.bytes;
     if (launches) launches[op.cls] += op.launches;
   }
+  return 0;
+}
+
+int cap4d_b200_unet_num_params(void* handle, int* n) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *n = static_cast<int>(u->expected_params().size());
+  return 0;
+}
+
+int cap4d_b200_unet_param_info(void* handle, int index, char* name, int name_capacity, int64_t* shape, int* ndim) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || name == nullptr || shape == nullptr || ndim == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  auto v = u->expected_params();
+  if (index < 0 || index >= static_cast<int>(v.size())) {
+    set_error("parameter index out of range");
+    return 1;
+  }
+  if (static_cast<int>(v[index].first.size()) + 1 > name_capacity) {
+    set_error("name buffer too small");
+    return 1;
+  }
+  std::strcpy(name, v[index].first.c_str());
+  *ndim = static_cast<int>(v[index].second.size());
+  for (int i = 0; i < *ndim; ++i) shape[i] = v[index].second[i];
   return 0;
 }
 

@@ -58,6 +58,10 @@ def _find_unet(model) -> B200MMDMUnet:
                     "(see cap4d_b200.unet.install)")
 
 
+class _SamplerState:
+    """Device-resident state of one sample() call."""
+
+
 class _CudaBackend:
     """The product data path: U-Net forward and fused CFG+DDIM update in libcap4d_b200.so."""
 
@@ -113,61 +117,84 @@ class B200StochasticIOSampler:
     def sample(self, S: int, ref_cond: Dict[str, torch.Tensor], ref_uncond: Dict[str, torch.Tensor],
                gen_cond: Dict[str, torch.Tensor], gen_uncond: Dict[str, torch.Tensor],
                latent_shape: Tuple[int, int, int], V: int = 8, R_max: int = 4, cfg_scale: float = 1.0,
-               eta: float = 0.0, verbose: bool = False, step_callback=None) -> torch.Tensor:
-        dev = self.backend.device
-        mem_device = next(iter(gen_cond.values())).device
-        n_gen = next(iter(gen_cond.values())).shape[0]
-        n_all_ref = next(iter(ref_cond.values())).shape[0]
-        R = min(n_all_ref, R_max)
-        G = V - R
-        assert n_gen % G == 0, f"number of generated images ({n_gen}) has to be divisible by G ({G})"
-        n_its = n_gen // G
-        steps, x_factors, e_factors = ddim_factors(self.main_model.alphas_cumprod, S, eta)
+               eta: float = 0.0, verbose: bool = False) -> torch.Tensor:
+        """Same contract as StochasticIOSampler.sample (sampler.py:64-233)."""
+        st = self.begin(S, ref_cond, ref_uncond, gen_cond, gen_uncond, latent_shape, V=V, R_max=R_max,
+                        cfg_scale=cfg_scale, eta=eta)
+        while st.i < st.n_steps:
+            self.step(st)
+        return self.end(st)
 
+    # The three phases of sample(), exposed so that a caller (bench.py) can time the steady state:
+    # begin = schedule + x_T + one-time upload, step = one DDIM step over all views, end = download.
+    @torch.no_grad()
+    def begin(self, S, ref_cond, ref_uncond, gen_cond, gen_uncond, latent_shape, V=8, R_max=4, cfg_scale=1.0,
+              eta=0.0) -> "_SamplerState":
+        st = _SamplerState()
+        dev = self.backend.device
+        st.mem_device = next(iter(gen_cond.values())).device
+        st.n_gen = next(iter(gen_cond.values())).shape[0]
+        st.n_all_ref = next(iter(ref_cond.values())).shape[0]
+        st.V, st.R = V, min(st.n_all_ref, R_max)
+        st.G = V - st.R
+        assert st.n_gen % st.G == 0, \
+            f"number of generated images ({st.n_gen}) has to be divisible by G ({st.G})"  # sampler.py:108
+        st.n_its = st.n_gen // st.G
+        st.steps, st.x_factors, st.e_factors = ddim_factors(self.main_model.alphas_cumprod, S, eta)
+        st.n_steps = len(st.steps)
+        st.cfg_scale = float(cfg_scale)
         # same generator, same call as the reference (sampler.py:112)
-        all_x = torch.randn((n_gen, *latent_shape), device=mem_device)
+        all_x = torch.randn((st.n_gen, *latent_shape), device=st.mem_device)
         if all_x.device != dev:
             self.h2d_bytes += all_x.numel() * 4
-        latents = all_x.to(dev).contiguous()
-        rc, ru = self._upload(ref_cond, dev), self._upload(ref_uncond, dev)
-        gc, gu = self._upload(gen_cond, dev), self._upload(gen_uncond, dev)
-        chw = int(np.prod(latent_shape))
+        st.latents = all_x.to(dev).contiguous()
+        st.rc, st.ru = self._upload(ref_cond, dev), self._upload(ref_uncond, dev)
+        st.gc, st.gu = self._upload(gen_cond, dev), self._upload(gen_uncond, dev)
+        st.chw = int(np.prod(latent_shape))
+        st.i = 0
+        return st
+
+    @torch.no_grad()
+    def step(self, st: "_SamplerState") -> None:
+        dev = self.backend.device
         dist, rank, world = self._dist()
+        n_its, R, V = st.n_its, st.R, st.V
+        step = st.steps[st.i]
+        # permutations: identical numpy consumption to sampler.py:131-139 (on every rank)
+        if R == 1:
+            ref_batches = np.zeros((n_its, R), dtype=np.int64)
+        else:
+            ref_batches = np.stack([np.random.permutation(np.arange(st.n_all_ref))[:R] for _ in range(n_its)], axis=0)
+        gen_batches = np.reshape(np.random.permutation(np.arange(st.n_gen)), (n_its, -1))
+        my_groups = np.arange(rank, n_its, world)  # round-robin like sampler.py:151-158
+        x_f, e_f = float(st.x_factors[st.i]), float(st.e_factors[st.i])
+        rc, ru, gc, gu, latents = st.rc, st.ru, st.gc, st.gu, st.latents
 
-        for i, step in enumerate(steps):
-            # permutations: identical numpy consumption to sampler.py:131-139 (on every rank)
-            if R == 1:
-                ref_batches = np.zeros((n_its, R), dtype=np.int64)
-            else:
-                ref_batches = np.stack([np.random.permutation(np.arange(n_all_ref))[:R] for _ in range(n_its)], axis=0)
-            gen_batches = np.reshape(np.random.permutation(np.arange(n_gen)), (n_its, -1))
-            my_groups = np.arange(rank, n_its, world)  # round-robin like sampler.py:151-158
-            x_f, e_f = float(x_factors[i]), float(e_factors[i])
+        for c0 in range(0, len(my_groups), self.groups_per_call):
+            grp = my_groups[c0:c0 + self.groups_per_call]
+            n = len(grp)
+            ref_idx = torch.from_numpy(ref_batches[grp]).to(dev, non_blocking=True)                       # [n, R]
+            gen_idx = torch.from_numpy(np.ascontiguousarray(gen_batches[grp])).to(dev, non_blocking=True)  # [n, G]
+            control = {}
+            for key in rc:
+                cond = torch.cat([rc[key][ref_idx], gc[key][gen_idx]], dim=1)
+                unc = torch.cat([ru[key][ref_idx], gu[key][gen_idx]], dim=1)
+                control[key] = torch.cat([unc, cond], dim=0)                                              # [2n, V, ...]
+            x_in = torch.cat([rc["z_input"][ref_idx], latents[gen_idx]], dim=1)
+            x_in = torch.cat([x_in, x_in], dim=0)
+            t_in = torch.full((2 * n, V), int(step), device=dev, dtype=torch.long)
+            eps = self.backend.eps(x_in, t_in, control)
+            self.unet_calls += 1
+            self.backend.cfg_ddim_update(latents, eps, gen_idx, n, V, R, st.chw, st.cfg_scale, x_f, e_f)
 
-            for c0 in range(0, len(my_groups), self.groups_per_call):
-                grp = my_groups[c0:c0 + self.groups_per_call]
-                n = len(grp)
-                ref_idx = torch.from_numpy(ref_batches[grp]).to(dev, non_blocking=True)   # [n, R]
-                gen_idx = torch.from_numpy(np.ascontiguousarray(gen_batches[grp])).to(dev, non_blocking=True)  # [n, G]
-                control = {}
-                for key in rc:
-                    cond = torch.cat([rc[key][ref_idx], gc[key][gen_idx]], dim=1)
-                    unc = torch.cat([ru[key][ref_idx], gu[key][gen_idx]], dim=1)
-                    control[key] = torch.cat([unc, cond], dim=0)                          # [2n, V, ...]
-                x_in = torch.cat([rc["z_input"][ref_idx], latents[gen_idx]], dim=1)
-                x_in = torch.cat([x_in, x_in], dim=0)
-                t_in = torch.full((2 * n, V), int(step), device=dev, dtype=torch.long)
-                eps = self.backend.eps(x_in, t_in, control)
-                self.unet_calls += 1
-                self.backend.cfg_ddim_update(latents, eps, gen_idx, n, V, R, chw, cfg_scale, x_f, e_f)
+        if world > 1:
+            self._exchange(dist, rank, world, latents, gen_batches, n_its, st.G, st.chw)
+        st.i += 1
 
-            if world > 1:
-                self._exchange(dist, rank, world, latents, gen_batches, n_its, G, chw)
-            if step_callback is not None:
-                step_callback(i, latents)
-
-        out = latents.to(mem_device)
-        if out.device != dev:
+    @torch.no_grad()
+    def end(self, st: "_SamplerState") -> torch.Tensor:
+        out = st.latents.to(st.mem_device)
+        if out.device != st.latents.device:
             self.d2h_bytes += out.numel() * 4
         return out
 

@@ -87,6 +87,54 @@ class B200MMDMUnet(torch.nn.Module):
                 )
             _lib.check(self._lib.cap4d_b200_unet_finalize(self._handle), "unet_finalize")
 
+    @staticmethod
+    def param_shapes(config: Mapping) -> Dict[str, tuple]:
+        """state_dict keys -> shapes of MMDMUnetModel for `config` (host-only; no GPU needed)."""
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        cfg = _make_config(config)
+        _lib.check(lib.cap4d_b200_unet_create(ctypes.byref(cfg), ctypes.byref(h)), "unet_create")
+        try:
+            n = ctypes.c_int()
+            _lib.check(lib.cap4d_b200_unet_num_params(h, ctypes.byref(n)), "num_params")
+            out = {}
+            name = ctypes.create_string_buffer(256)
+            shape = (ctypes.c_int64 * 4)()
+            nd = ctypes.c_int()
+            for i in range(n.value):
+                _lib.check(lib.cap4d_b200_unet_param_info(h, i, name, 256, shape, ctypes.byref(nd)), "param_info")
+                out[name.value.decode()] = tuple(int(shape[k]) for k in range(nd.value))
+            return out
+        finally:
+            lib.cap4d_b200_unet_destroy(h)
+
+    @classmethod
+    def random_init(cls, config: Mapping, seed: int = 0, device=None, zero_std: float = 0.02) -> "B200MMDMUnet":
+        """Synthetic weights of the right architecture, generated on the GPU (benchmarks; there is no
+        network for checkpoints).  Layers the reference zero-initialises get N(0, zero_std) so the
+        network output is not identically zero (SURVEY.md note Z)."""
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd = {}
+        for name, shape in cls.param_shapes(config).items():
+            is_norm = name.startswith("out.0.") or any(
+                k in name for k in (".in_layers.0.", ".out_layers.0.", ".norm.", ".norm1.", ".norm3."))
+            is_zero = name.startswith(("out.2.", "cond_linear.")) or any(
+                k in name for k in (".out_layers.3.", ".proj_out.", ".attn1.to_out.0."))
+            if is_norm:
+                t = (1.0 if name.endswith("weight") else 0.0) + 0.1 * torch.randn(shape, generator=g, device=dev)
+            elif is_zero:
+                t = zero_std * torch.randn(shape, generator=g, device=dev)
+            elif name.endswith("bias"):
+                t = 0.05 * torch.randn(shape, generator=g, device=dev)
+            else:
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) / (fan_in ** 0.5)
+            sd[name] = t
+        return cls(config, sd, device=dev)
+
     @classmethod
     def from_reference(cls, ref_unet, device=None) -> "B200MMDMUnet":
         return cls(config_from_reference(ref_unet), ref_unet.state_dict(), device=device)
@@ -139,22 +187,43 @@ class B200MMDMUnet(torch.nn.Module):
             raise ValueError("channel count mismatch")
         return xs, t, z, m, p
 
+    # every `record_every`-th forward records CUDA events around its launches (no synchronisation);
+    # collect_timings() returns the per-class sums.  0 = off.
+    record_every = 0
+    _calls = 0
+
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, control=None, **kwargs):
         assert context is None  # mmdm_unet.py:85
         xs, t, z, m, p = self._prep(x, timesteps, control)
         B, V, C, H, W = xs.shape
         out = torch.empty((B, V, self.config["out_channels"], H, W), dtype=torch.float32, device=self._device)
+        self._calls += 1
         with torch.cuda.device(self._device):
             ws = self._workspace(B, V, H, W)
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(
-                self._lib.cap4d_b200_unet_forward(self._handle, xs.data_ptr(), t.data_ptr(), z.data_ptr(), m.data_ptr(),
-                                                  p.data_ptr(), out.data_ptr(), B, V, H, W, ws.data_ptr(), ws.numel(),
-                                                  ctypes.c_void_p(stream)),
-                "unet_forward",
-            )
+            if self.record_every and self._calls % self.record_every == 0:
+                _lib.check(
+                    self._lib.cap4d_b200_unet_forward_timed(self._handle, xs.data_ptr(), t.data_ptr(), z.data_ptr(),
+                                                            m.data_ptr(), p.data_ptr(), out.data_ptr(), B, V, H, W,
+                                                            ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream), None),
+                    "unet_forward_timed",
+                )
+            else:
+                _lib.check(
+                    self._lib.cap4d_b200_unet_forward(self._handle, xs.data_ptr(), t.data_ptr(), z.data_ptr(),
+                                                      m.data_ptr(), p.data_ptr(), out.data_ptr(), B, V, H, W,
+                                                      ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
+                    "unet_forward",
+                )
         return out.to(dtype=x.dtype) if x.dtype != torch.float32 else out
+
+    def collect_timings(self):
+        """Per-class ms summed over the recorded forwards since the last call -> ({class: ms}, n_forwards)."""
+        ms = (ctypes.c_float * _lib.N_CLASSES)()
+        n = ctypes.c_int()
+        _lib.check(self._lib.cap4d_b200_unet_collect_timings(self._handle, ms, ctypes.byref(n)), "collect_timings")
+        return {c: float(ms[i]) for i, c in enumerate(_lib.CLASS_NAMES)}, n.value
 
     @torch.no_grad()
     def forward_timed(self, x, timesteps, control):

@@ -54,6 +54,11 @@ int cap4d_b200_unet_create(const cap4d_b200_unet_config* cfg, void** handle);
  * (e.g. "input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight"), `data` fp32 on host or device. */
 int cap4d_b200_unet_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim);
 
+/* Parameter census of the topology (= the keys and shapes of the reference module's state_dict,
+ * e.g. 576 tensors / 815 549 764 elements for cap4d_mmdm_final.yaml).  shape must hold 4 entries. */
+int cap4d_b200_unet_num_params(void* handle, int* n);
+int cap4d_b200_unet_param_info(void* handle, int index, char* name, int name_capacity, int64_t* shape, int* ndim);
+
 /* Repack all weights for the tensor-core kernels (bf16, K-major, fused QKV / GEGLU / skip-conv
  * layouts).  Fails if any parameter of the topology was not loaded. */
 int cap4d_b200_unet_finalize(void* handle);
@@ -70,7 +75,10 @@ int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timeste
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Instrumentation (no reference counterpart): kernels launched per forward, algorithmic FLOPs per
- * forward by class, and a forward with CUDA-event timing per kernel class.
+ * forward by class, and a forward with CUDA events around every launch.  forward_timed with
+ * class_ms != NULL synchronises the stream and returns the per-class ms of that call; with
+ * class_ms == NULL it only records the events (no synchronisation, usable inside a timed region)
+ * and collect_timings() later returns the per-class sums over all such calls.
  * classes: 0 conv3x3 (tcgen05 implicit GEMM), 1 linear (tcgen05 GEMM), 2 attention core,
  *          3 GroupNorm, 4 LayerNorm, 5 other (pack / mix / resample / embedding). */
 #define CAP4D_B200_N_CLASSES 6
@@ -79,6 +87,8 @@ int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int*
 int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
                                   const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H,
                                   int W, void* workspace, size_t workspace_bytes, void* stream, float* class_ms);
+
+int cap4d_b200_unet_collect_timings(void* handle, float* class_ms, int* n_runs);
 
 int cap4d_b200_unet_destroy(void* handle);
 
