@@ -63,6 +63,8 @@ SIGNATURES = {
                 c_void_p, POINTER(c_float), c_int]),
     "cap4d_b200_attention_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, POINTER(c_float), c_int]),
+    "cap4d_b200_attention_trace": (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "cap4d_b200_groupnorm_bf16": (
         c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
                 c_void_p, c_void_p, POINTER(c_float), c_int]),

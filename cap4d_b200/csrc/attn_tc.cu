@@ -6,13 +6,18 @@
 // invariant to the order of the keys, so the '(n t)' interleave of the reference is not reproduced:
 // a sequence is simply the contiguous token rows [s*L, (s+1)*L) of the fused QKV matrix.
 //
-// One CTA = one 128-row Q tile of one (sequence, head).  192 threads:
-//   warp 0    TMA producer (Q once, K/V tiles through two 3-deep rings)
-//   warp 1    MMA issuer: S_j = Q K_j^T (128x128, TMEM, double buffered), PV_j = P_j V_j (128x64, TMEM)
-//   warps 2-5 softmax: thread <-> query row; S row TMEM->registers, online max/sum with exp2,
-//             P_j -> bf16 -> shared memory in the UMMA K-major 128B-swizzle layout, O accumulated
-//             in registers from the PV_j partial products (rescaled FA2-style).
-// V is consumed straight from its row-major [kv][64] TMA tile as an MN-major B operand.
+// One CTA = two 128-row Q tiles (A, B) of one (sequence, head).  384 threads:
+//   WG0  warp 0 TMA producer (Q once, K/V tiles through two 4-deep rings), warps 1 / 3 MMA issuers of Q tile
+//        A / B, warp 2 TMEM owner; registers trimmed to 56/thread (setmaxnreg) and handed to the softmax warpgroups.
+//   WG1/WG2  softmax of Q tile A/B: thread <-> query row.
+// Everything between the two GEMMs stays in tensor memory (512 columns: S_A S_B | O_A O_B | P_A P_B):
+//   S_X(j) = Q_X K_j^T (SS MMA, fp32)  ->  registers (S_X is released to the tensor core at once, so QK of
+//   tile j+1 overlaps the exponentials of tile j)  ->  P_X(j) = exp2(S - m) as bf16x2 back into TMEM
+//   (tcgen05.st)  ->  O_X += P_X(j) V_j (TS MMA: A operand from TMEM, V straight from its row-major TMA
+//   tile as an MN-major B operand).  O_X accumulates in TMEM over all KV tiles and is rescaled lazily
+//   (only when a row max grows by more than 2^8), so the steady-state softmax is: load S, max, 128
+//   exp2, pack, store P.  The exponentials are MUFU-bound (16/clk/SM); two warpgroups keep the MUFU
+//   busy while the other one loads / stores.
 #include <cstdio>
 #include <cstring>
 
@@ -26,23 +31,28 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
 
 namespace {
 
-constexpr int BQ = 128;   // query rows per CTA
+constexpr int BQ = 128;   // query rows per softmax warpgroup (one UMMA M tile)
+constexpr int NQT = 2;    // Q tiles per CTA
 constexpr int BKV = 128;  // keys per tile
 constexpr int HD = 64;    // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KiB: one Q / K / V tile
-constexpr int P_BYTES = BQ * BKV * 2;     // 32 KiB
-constexpr int KS = 3, VS = 3;
-constexpr int ATTN_THREADS = 192;
+constexpr int KS = 4, VS = 4;
+constexpr int ATTN_THREADS = 384;         // WG0: TMA / MMA / TMEM owner; WG1, WG2: softmax of Q tile A, B
 constexpr int TM_COLS = 512;
-constexpr int TM_S0 = 0, TM_S1 = 128, TM_PV = 256;
+constexpr int TM_S = 0;     // S_X (fp32 128x128)   at   0 + 128 x
+constexpr int TM_O = 256;   // O_X (fp32 128x64)    at 256 +  64 x
+constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
+constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 224;  // 128*56 + 256*224 = 64512 <= 65536
+constexpr float RESCALE_LOG2 = 8.0f;  // O / l are only rescaled when the row max grew by more than 2^8
 
 struct AttnBars {
   uint64_t q_full;
   uint64_t k_full[KS], k_empty[KS];
   uint64_t v_full[VS], v_empty[VS];
-  uint64_t s_full[2];
-  uint64_t p_full[2];
-  uint64_t pv_full;
+  uint64_t s_full[NQT];   // MMA -> softmax: S_X(j) is in TMEM
+  uint64_t s_free[NQT];   // softmax -> MMA: S_X(j) has been read into registers
+  uint64_t p_full[NQT];   // softmax -> MMA: P_X(j) is in TMEM (and O_X has been rescaled if needed)
+  uint64_t pv_full[NQT];  // MMA -> softmax: O_X += P_X(j) V_j is complete
   uint32_t tmem_base;
 };
 
@@ -52,28 +62,133 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 struct AttnParams {
   int C, L, heads;
   int nkv;
   float scale_log2;
   bf16* out;
+  long long* trace;  // TRACE builds only: [2 softmax WGs + 1 MMA][TRACE_J][8] clock64 stamps of CTA (0,0,0)
 };
 
+constexpr int TRACE_J = 16;
+#define ATTN_STAMP(slot)                                                                            \
+  do {                                                                                              \
+    if (TRACE && trace != nullptr && j < TRACE_J) trace[(static_cast<size_t>(x) * TRACE_J + j) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+// One KV tile of the online softmax for one query row (thread).  MASK: only the first `valid` keys count.
+// m_used is the stabiliser the running sum l and the TMEM accumulator O_X are expressed in; it only
+// follows the true row max when that grew by more than 2^RESCALE_LOG2 (P stays <= 2^8, exact in fp32/bf16
+// range), so the O rescale - a TMEM round trip - is rare after the first tiles.
+template <bool MASK, bool TRACE>
+__device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int j, uint32_t s_addr, uint32_t o_addr,
+                                             uint32_t p_addr, float scale_log2, int valid, float& m_used,
+                                             float& l_run, long long* trace) {
+  ATTN_STAMP(0);
+  mbar_wait(&bars->s_full[x], j & 1);
+  tc_fence_after();
+  ATTN_STAMP(1);
+  float s[BKV];
+  {
+    uint32_t* su = reinterpret_cast<uint32_t*>(s);
+    tmem_ld32(s_addr, su);
+    tmem_ld32(s_addr + 32, su + 32);
+    tmem_ld32(s_addr + 64, su + 64);
+    tmem_ld32(s_addr + 96, su + 96);
+    tmem_ld_wait();
+  }
+  tc_fence_before();
+  mbar_arrive(&bars->s_free[x]);  // the tensor core may overwrite S_X with tile j+1 now
+  ATTN_STAMP(2);
+  if (MASK) {
+#pragma unroll
+    for (int i = 0; i < BKV; ++i)
+      if (i >= valid) s[i] = -INFINITY;
+  }
+  float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+  for (int i = 4; i < BKV; i += 4) {
+    mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+    mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+  }
+  const float m_new = fmaxf(m_used, fmaxf(mx0, mx1) * scale_log2);
+  bool pv_waited = (j == 0);
+  if (j == 0) {
+    m_used = m_new;  // O_X is still empty: nothing to rescale
+  } else {
+    const bool grow = (m_new - m_used) > RESCALE_LOG2;
+    if (__any_sync(0xffffffffu, grow)) {
+      // rare: O_X must be rescaled, which needs O_X += P_X(j-1) V_(j-1) to be complete
+      mbar_wait(&bars->pv_full[x], (j - 1) & 1);
+      tc_fence_after();
+      pv_waited = true;
+      const float f = grow ? ex2f(m_used - m_new) : 1.0f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t ov[32];
+        tmem_ld32(o_addr + h * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+        tmem_st32(o_addr + h * 32, ov);
+      }
+      l_run *= f;
+      if (grow) m_used = m_new;
+    }
+  }
+  ATTN_STAMP(3);
+  float rs0 = 0.f, rs1 = 0.f;
+  uint32_t pk[BKV / 2];
+#pragma unroll
+  for (int i = 0; i < BKV; i += 2) {
+    const float p0 = ex2f(fmaf(s[i], scale_log2, -m_used));
+    const float p1 = ex2f(fmaf(s[i + 1], scale_log2, -m_used));
+    rs0 += p0;
+    rs1 += p1;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  l_run += rs0 + rs1;
+  ATTN_STAMP(4);
+  if (!pv_waited) {
+    // P_X may only be overwritten once the PV MMA of tile j-1 has consumed it (long done by now)
+    mbar_wait(&bars->pv_full[x], (j - 1) & 1);
+    tc_fence_after();
+  }
+  // P_X(j) -> TMEM as the A operand of the PV MMA: lane = query row, column c = keys (2c, 2c+1) as bf16x2
+  tmem_st32(p_addr, pk);
+  tmem_st32(p_addr + 32, pk + 32);
+  tmem_st_wait();
+  ATTN_STAMP(5);
+  tc_fence_before();
+  mbar_arrive(&bars->p_full[x]);
+  ATTN_STAMP(6);
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sQ = smem;                      // [NQT] tiles
+  uint8_t* sK = sQ + NQT * TILE_BYTES;
   uint8_t* sV = sK + KS * TILE_BYTES;
-  uint8_t* sP = sV + VS * TILE_BYTES;
-  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 2 * P_BYTES);
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sV + VS * TILE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row_base = seq * p.L;  // first token row of this sequence
-  const int q0 = qt * BQ;
+  const int q0 = qt * (NQT * BQ);
   const int nkv = p.nkv;
 
   if (warp == 0 && lane == 0) {
@@ -81,20 +196,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->k_empty[i], NQT);  // one commit per MMA issuer
     }
     for (int i = 0; i < VS; ++i) {
       mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->v_empty[i], NQT);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NQT; ++i) {
       mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_free[i], 128);
       mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->pv_full[i], 1);
     }
-    mbar_init(&bars->pv_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(&bars->tmem_base, TM_COLS);
     tmem_relinquish();
   }
@@ -103,11 +219,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tmQKV, &bars->q_full, head * HD, row_base + q0);
+  if (wg == 0) {
+    setmaxnreg_dec<REGS_CTRL>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_arrive_expect_tx(&bars->q_full, NQT * TILE_BYTES);
+      for (int x = 0; x < NQT; ++x)
+        tma_load_2d(sQ + x * TILE_BYTES, &tmQKV, &bars->q_full, head * HD, row_base + q0 + x * BQ);
       for (int j = 0; j < nkv; ++j) {
         const int ks = j % KS, vs = j % VS;
         mbar_wait(&bars->k_empty[ks], ((j / KS) & 1) ^ 1);
@@ -117,153 +235,102 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * p.C + head * HD, row_base + j * BKV);
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    } else if ((warp == 1 || warp == 3) && lane == 0) {
+      // ===================== MMA issuers: warp 1 -> Q tile A, warp 3 -> Q tile B =====================
+      // (one issuing thread per Q tile: the mbarrier round trips of one tile's chain do not delay the other's)
+      const int x = warp >> 1;
       const uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0);  // B = K tile, K-major (d contiguous)
-      const uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 1);   // B = V tile, MN-major (d contiguous, k = kv row)
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ));
+      const uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 1);   // A = P in TMEM; B = V tile, MN-major
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
+      const uint32_t s_tmem = tmem_base + TM_S + x * BKV;
+      const uint32_t o_tmem = tmem_base + TM_O + x * HD;
+      const uint32_t p_tmem = tmem_base + TM_P + x * (BKV / 2);
+      long long* trace = (TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && x == 0) ? p.trace : nullptr;
       mbar_wait(&bars->q_full, 0);
+      // S_X(j) = Q_X K_j^T; K stage j is released when both issuers have committed
       auto issue_qk = [&](int j) {
         const int ks = j % KS;
         mbar_wait(&bars->k_full[ks], (j / KS) & 1);
+        if (j > 0) mbar_wait(&bars->s_free[x], (j - 1) & 1);  // S_X(j-1) is in registers
         tc_fence_after();
         const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES));
-        const uint32_t d = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(s_tmem, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&bars->s_full[x]);
         umma_commit(&bars->k_empty[ks]);
-        umma_commit(&bars->s_full[j & 1]);
       };
       issue_qk(0);
       for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) issue_qk(j + 1);  // S buffer (j+1)&1 was released by p_full of tile j-1
+        if (TRACE && trace != nullptr && j < TRACE_J) trace[(static_cast<size_t>(2) * TRACE_J + j) * 8 + 0] = clock64();
+        if (j + 1 < nkv) issue_qk(j + 1);
+        if (TRACE && trace != nullptr && j < TRACE_J) trace[(static_cast<size_t>(2) * TRACE_J + j) * 8 + 1] = clock64();
         const int vs = j % VS;
-        mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);
         mbar_wait(&bars->v_full[vs], (j / VS) & 1);
+        mbar_wait(&bars->p_full[x], j & 1);
         tc_fence_after();
-        const uint64_t pdesc0 = umma_smem_desc_sw128(smem_u32(sP + (j & 1) * P_BYTES));
-        const uint64_t pdesc1 = umma_smem_desc_sw128(smem_u32(sP + (j & 1) * P_BYTES + TILE_BYTES));
         const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES));
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          // A: P sub-tile kk/4 (64 keys each), 32 B per k16 step; B: 16 kv rows = 2048 B per step
-          const uint64_t ad = ((kk < 4) ? pdesc0 : pdesc1) + 2 * (kk & 3);
+          // A: 16 keys = 8 TMEM columns per step; B: 16 kv rows = 2048 B per step
           const uint64_t bd = vdesc + static_cast<uint64_t>((kk * 16 * 128) >> 4);
-          umma_bf16(tmem_base + TM_PV, ad, bd, idesc_pv, kk != 0);
+          umma_bf16_ts(o_tmem, p_tmem + kk * 8, bd, idesc_pv, (j | kk) != 0);
         }
+        umma_commit(&bars->pv_full[x]);
         umma_commit(&bars->v_empty[vs]);
-        umma_commit(&bars->pv_full);
+        if (TRACE && trace != nullptr && j < TRACE_J) trace[(static_cast<size_t>(2) * TRACE_J + j) * 8 + 2] = clock64();
       }
     }
   } else {
-    // ===================== softmax + O accumulation (warps 2..5) =====================
+    // ===================== softmax: WG1 -> Q tile 0, WG2 -> Q tile 1 =====================
+    setmaxnreg_inc<REGS_SOFTMAX>();
+    const int x = wg - 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the Q tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
+    const uint32_t s_addr = tmem_base + lane_addr + TM_S + x * BKV;
+    const uint32_t o_addr = tmem_base + lane_addr + TM_O + x * HD;
+    const uint32_t p_addr = tmem_base + lane_addr + TM_P + x * (BKV / 2);
+    float m_used = -INFINITY, l_run = 0.f;
     const int valid_last = p.L - (nkv - 1) * BKV;  // valid keys in the last tile (1..128)
 
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      float s[BKV];
-      {
-        const uint32_t ta = tmem_base + lane_addr + ((j & 1) ? TM_S1 : TM_S0);
-        uint32_t* su = reinterpret_cast<uint32_t*>(s);
-        tmem_ld32(ta, su);
-        tmem_ld32(ta + 32, su + 32);
-        tmem_ld32(ta + 64, su + 64);
-        tmem_ld32(ta + 96, su + 96);
-        tmem_ld_wait();
-      }
-      if (j == nkv - 1 && valid_last < BKV) {
-#pragma unroll
-        for (int i = 0; i < BKV; ++i)
-          if (i >= valid_last) s[i] = -INFINITY;
-      }
-      float mx = s[0];
-#pragma unroll
-      for (int i = 1; i < BKV; ++i) mx = fmaxf(mx, s[i]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2f(m_run - m_new);
-      float rowsum = 0.f;
-      uint32_t pk[BKV / 2];
-#pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
-        const float p0 = ex2f(fmaf(s[i], p.scale_log2, -m_new));
-        const float p1 = ex2f(fmaf(s[i + 1], p.scale_log2, -m_new));
-        rowsum += p0 + p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-      }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-
-      // fold the previous tile's P V product into O (also frees P buffer / PV columns for reuse)
-      if (j > 0) {
-        mbar_wait(&bars->pv_full, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pv[32];
-          tmem_ld32(tmem_base + lane_addr + TM_PV + h * 32, pv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_pending, __uint_as_float(pv[i]));
-        }
-      }
-      alpha_pending = alpha;
-
-      // P_j -> smem, K-major SW128: row r, 16-byte chunk c of sub-tile t at (c ^ (r & 7)) * 16
-      {
-        uint8_t* prow = sP + (j & 1) * P_BYTES + r * 128;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 u = make_uint4(pk[t * 32 + c * 4], pk[t * 32 + c * 4 + 1], pk[t * 32 + c * 4 + 2],
-                                 pk[t * 32 + c * 4 + 3]);
-            *reinterpret_cast<uint4*>(prow + t * TILE_BYTES + ((c ^ (r & 7)) << 4)) = u;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bars->p_full[j & 1]);
-    }
-    // last partial product
-    mbar_wait(&bars->pv_full, (nkv - 1) & 1);
+    // the key mask costs 2 ALU ops per score, so it is compiled only into the (peeled) last tile
+    const bool tail = valid_last < BKV;
+    const int n_main = tail ? nkv - 1 : nkv;
+    long long* trace = nullptr;
+    if (TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 127) == 0) trace = p.trace;
+    for (int j = 0; j < n_main; ++j)
+      softmax_tile<false, TRACE>(bars, x, j, s_addr, o_addr, p_addr, p.scale_log2, BKV, m_used, l_run, trace);
+    if (tail)
+      softmax_tile<true, TRACE>(bars, x, nkv - 1, s_addr, o_addr, p_addr, p.scale_log2, valid_last, m_used, l_run,
+                                trace);
+    // O_X is complete once the last PV MMA has landed
+    mbar_wait(&bars->pv_full[x], (nkv - 1) & 1);
     tc_fence_after();
+    const int qrow = q0 + x * BQ + r;
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.out + static_cast<size_t>(row_base + qrow) * p.C + head * HD;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      uint32_t pv[32];
-      tmem_ld32(tmem_base + lane_addr + TM_PV + h * 32, pv);
+      uint32_t ov[32];
+      tmem_ld32(o_addr + h * 32, ov);
       tmem_ld_wait();
+      if (qrow < p.L) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_pending, __uint_as_float(pv[i]));
-    }
-    if (q0 + r < p.L) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = p.out + static_cast<size_t>(row_base + q0 + r) * p.C + head * HD;
-#pragma unroll
-      for (int i = 0; i < HD; i += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-        u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-        u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-        u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + i) = u;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + h * 32 + i) = u;
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
   }
@@ -284,8 +351,8 @@ bool make_attn_plan(AttnPlan* plan, const bf16* qkv, bf16* out, int M, int C, in
   plan->heads = C / HD;
   plan->out = out;
   plan->scale_log2 = scale * 1.4426950408889634f;
-  plan->grid = dim3((L + BQ - 1) / BQ, plan->heads, plan->n_seq);
-  plan->smem_bytes = TILE_BYTES * (1 + KS + VS) + 2 * P_BYTES + sizeof(AttnBars) + 1024;
+  plan->grid = dim3((L + NQT * BQ - 1) / (NQT * BQ), plan->heads, plan->n_seq);
+  plan->smem_bytes = TILE_BYTES * (NQT + KS + VS) + sizeof(AttnBars) + 1024;
   plan->flops = 4.0 * plan->n_seq * plan->heads * static_cast<double>(L) * L * HD;
   uint64_t dims[2] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(M)};
   uint64_t strides[2] = {1, static_cast<uint64_t>(3 * C)};
@@ -293,10 +360,12 @@ bool make_attn_plan(AttnPlan* plan, const bf16* qkv, bf16* out, int M, int C, in
   return make_tmap_bf16(&plan->tmQKV, qkv, 2, dims, strides, box);
 }
 
-cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream) {
+cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* trace) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -307,7 +376,11 @@ cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   p.nkv = (plan.L + BKV - 1) / BKV;
   p.scale_log2 = plan.scale_log2;
   p.out = plan.out;
-  attn_tc_kernel<<<plan.grid, ATTN_THREADS, plan.smem_bytes, stream>>>(plan.tmQKV, p);
+  p.trace = trace;
+  if (trace != nullptr)
+    attn_tc_kernel<true><<<plan.grid, ATTN_THREADS, plan.smem_bytes, stream>>>(plan.tmQKV, p);
+  else
+    attn_tc_kernel<false><<<plan.grid, ATTN_THREADS, plan.smem_bytes, stream>>>(plan.tmQKV, p);
   return cudaGetLastError();
 }
 

@@ -97,7 +97,8 @@ struct AttnPlan {
   double flops;  // 4 * n_seq * heads * L * L * 64
 };
 bool make_attn_plan(AttnPlan* plan, const bf16* qkv, bf16* out, int M, int C, int L, float scale);
-cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream);
+// trace != nullptr: instrumented build, clock64 stamps of CTA (0,0,0): [3][16][8] (softmax A, softmax B, MMA thread)
+cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* trace = nullptr);
 
 // ---------------------------------------------------------------------------
 // Norms (norm.cu)

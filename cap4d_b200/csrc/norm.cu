@@ -17,7 +17,7 @@ namespace cap4d {
 namespace {
 
 constexpr int GN_GROUPS = 32;
-constexpr int GN_MAX_QI = 8;  // quads per thread along C (C <= 4 * 256 * 8)
+constexpr int GN_MAX_QI = 4;  // quads per thread along C (C <= 4 * 256 * 4 = 4096)
 
 struct GnGeom {
   int C, C1, quads, TX, TY, nqi, cpg;
@@ -30,12 +30,21 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw) {
   g.C1 = C1;
   g.quads = g.C / 4;
   g.cpg = g.C / GN_GROUPS;
-  int tx = 1;
-  for (int d = 1; d <= 256 && d <= g.quads; ++d)
-    if (g.quads % d == 0) tx = d;
-  g.TX = tx;
-  g.nqi = g.quads / tx;
-  g.TY = 256 / tx;
+  // per-thread quad count must be one of the instantiated template values {1, 2, 4}
+  g.TX = 0;
+  g.nqi = 0;
+  for (int nq = 1; nq <= 4; nq *= 2) {
+    if (g.quads % nq == 0 && g.quads / nq <= 256) {
+      g.nqi = nq;
+      g.TX = g.quads / nq;
+      break;
+    }
+  }
+  if (g.TX == 0) {  // unsupported (C > 4096 or odd quad count): reported by the launcher
+    g.TX = 1;
+    g.nqi = GN_MAX_QI + 1;
+  }
+  g.TY = 256 / g.TX;
   if (g.TY < 1) g.TY = 1;
   if (g.TY > hw) g.TY = hw;
   int rpc = (hw + GN_MAX_CHUNKS - 1) / GN_MAX_CHUNKS;
@@ -53,9 +62,13 @@ __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const fl
   return __ldg(reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1)));
 }
 
-// grid (n_chunks, n_img), block (TX, TY)
-__global__ void gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw,
-                                int nqi, int cpg, int rows_per_chunk, float* __restrict__ partial) {
+// ---- GroupNorm statistics -------------------------------------------------------------------
+// grid (n_chunks, n_img), block (TX, TY): thread (tx, ty) owns channel quads tx + i*TX (i < NQI) and
+// rows ty, ty+TY, ... of its chunk, UNROLL rows (= UNROLL*NQI independent 16 B loads) per iteration.
+template <int NQI, int UNROLL>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
+                int rows_per_chunk, float* __restrict__ partial) {
   extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
   const int C = C1 + C2;
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -63,32 +76,45 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, const float* __res
   const int tid = ty * TX + tx;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
-  float sum[GN_MAX_QI][4], sq[GN_MAX_QI][4];
+  float sum[NQI][4], sq[NQI][4];
 #pragma unroll
-  for (int qi = 0; qi < GN_MAX_QI; ++qi)
+  for (int qi = 0; qi < NQI; ++qi)
 #pragma unroll
     for (int k = 0; k < 4; ++k) sum[qi][k] = sq[qi][k] = 0.f;
-  for (int r = r0 + ty; r < r1; r += TY) {
-    const size_t row = static_cast<size_t>(n) * hw + r;
+  const size_t img_row = static_cast<size_t>(n) * hw;
+  int r = r0 + ty;
+  for (; r + (UNROLL - 1) * TY < r1; r += UNROLL * TY) {
+    float4 v[UNROLL][NQI];
 #pragma unroll
-    for (int qi = 0; qi < GN_MAX_QI; ++qi) {
-      if (qi < nqi) {
-        const float4 v = ld_quad(x1, x2, C1, C2, row, (tx + qi * TX) * 4);
-        sum[qi][0] += v.x; sq[qi][0] += v.x * v.x;
-        sum[qi][1] += v.y; sq[qi][1] += v.y * v.y;
-        sum[qi][2] += v.z; sq[qi][2] += v.z * v.z;
-        sum[qi][3] += v.w; sq[qi][3] += v.w * v.w;
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int qi = 0; qi < NQI; ++qi) {
+        sum[qi][0] += v[u][qi].x; sq[qi][0] = fmaf(v[u][qi].x, v[u][qi].x, sq[qi][0]);
+        sum[qi][1] += v[u][qi].y; sq[qi][1] = fmaf(v[u][qi].y, v[u][qi].y, sq[qi][1]);
+        sum[qi][2] += v[u][qi].z; sq[qi][2] = fmaf(v[u][qi].z, v[u][qi].z, sq[qi][2]);
+        sum[qi][3] += v[u][qi].w; sq[qi][3] = fmaf(v[u][qi].w, v[u][qi].w, sq[qi][3]);
       }
+  }
+  for (; r < r1; r += TY) {
+#pragma unroll
+    for (int qi = 0; qi < NQI; ++qi) {
+      const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4);
+      sum[qi][0] += v.x; sq[qi][0] = fmaf(v.x, v.x, sq[qi][0]);
+      sum[qi][1] += v.y; sq[qi][1] = fmaf(v.y, v.y, sq[qi][1]);
+      sum[qi][2] += v.z; sq[qi][2] = fmaf(v.z, v.z, sq[qi][2]);
+      sum[qi][3] += v.w; sq[qi][3] = fmaf(v.w, v.w, sq[qi][3]);
     }
   }
   float* my = s_ch + static_cast<size_t>(ty) * 2 * C;
 #pragma unroll
-  for (int qi = 0; qi < GN_MAX_QI; ++qi) {
-    if (qi < nqi) {
-      const int c = (tx + qi * TX) * 4;
-      *reinterpret_cast<float4*>(my + c) = make_float4(sum[qi][0], sum[qi][1], sum[qi][2], sum[qi][3]);
-      *reinterpret_cast<float4*>(my + C + c) = make_float4(sq[qi][0], sq[qi][1], sq[qi][2], sq[qi][3]);
-    }
+  for (int qi = 0; qi < NQI; ++qi) {
+    const int c = (tx + qi * TX) * 4;
+    *reinterpret_cast<float4*>(my + c) = make_float4(sum[qi][0], sum[qi][1], sum[qi][2], sum[qi][3]);
+    *reinterpret_cast<float4*>(my + C + c) = make_float4(sq[qi][0], sq[qi][1], sq[qi][2], sq[qi][3]);
   }
   __syncthreads();
   if (tid < GN_GROUPS) {
@@ -106,24 +132,41 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, const float* __res
   }
 }
 
-// grid (n_chunks, n_img), block (TX, TY)
-__global__ void gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw,
-                                int nqi, int cpg, int rows_per_chunk, int n_chunks,
-                                const float* __restrict__ partial, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int apply_silu, bf16* __restrict__ out,
-                                bf16* __restrict__ raw_out) {
+// ---- GroupNorm apply (+SiLU) ------------------------------------------------------------------
+template <int NQI, int UNROLL>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
+                int rows_per_chunk, int n_chunks, const float* __restrict__ partial,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int apply_silu,
+                bf16* __restrict__ out, bf16* __restrict__ raw_out) {
+  __shared__ double s_part[8][GN_GROUPS][2];
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   const int C = C1 + C2;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  const int tid = ty * TX + tx;
+  const int tid = ty * TX + tx, nthreads = TX * TY;
+  // fixed-order reduction of the per-chunk partials, spread over up to 8 warps: deterministic
+  const int nparts = min(8, max(1, nthreads / 32));
+  {
+    const int part = tid >> 5, g = tid & 31;
+    if (part < nparts) {
+      double s = 0.0, q = 0.0;
+      for (int ch = part; ch < n_chunks; ch += nparts) {
+        const float2 v =
+            *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + ch) * GN_GROUPS + g) * 2);
+        s += v.x;
+        q += v.y;
+      }
+      s_part[part][g][0] = s;
+      s_part[part][g][1] = q;
+    }
+  }
+  __syncthreads();
   if (tid < GN_GROUPS) {
-    // fixed-order reduction of the per-chunk partials: deterministic
     double s = 0.0, q = 0.0;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const float* src = partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + ch) * GN_GROUPS + tid) * 2;
-      s += src[0];
-      q += src[1];
+    for (int pt = 0; pt < nparts; ++pt) {
+      s += s_part[pt][tid][0];
+      q += s_part[pt][tid][1];
     }
     const double cnt = static_cast<double>(cpg) * hw;
     const double mean = s / cnt;
@@ -134,77 +177,84 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, const float* __res
   }
   __syncthreads();
   // per-thread affine: y = x * a + b with a = rstd*gamma, b = beta - mean*rstd*gamma
-  float a[GN_MAX_QI][4], b[GN_MAX_QI][4];
+  float a[NQI][4], b[NQI][4];
 #pragma unroll
-  for (int qi = 0; qi < GN_MAX_QI; ++qi) {
-    if (qi < nqi) {
-      const int c = (tx + qi * TX) * 4;
+  for (int qi = 0; qi < NQI; ++qi) {
+    const int c = (tx + qi * TX) * 4;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int g = (c + k) / cpg;
-        const float ga = __ldg(gamma + c + k), be = __ldg(beta + c + k);
-        a[qi][k] = s_rstd[g] * ga;
-        b[qi][k] = be - s_mean[g] * s_rstd[g] * ga;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int g = (c + k) / cpg;
+      const float ga = __ldg(gamma + c + k), be = __ldg(beta + c + k);
+      a[qi][k] = s_rstd[g] * ga;
+      b[qi][k] = be - s_mean[g] * s_rstd[g] * ga;
     }
   }
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
-  for (int r = r0 + ty; r < r1; r += TY) {
-    const size_t row = static_cast<size_t>(n) * hw + r;
-#pragma unroll
-    for (int qi = 0; qi < GN_MAX_QI; ++qi) {
-      if (qi < nqi) {
-        const int c = (tx + qi * TX) * 4;
-        const float4 v = ld_quad(x1, x2, C1, C2, row, c);
-        float y0 = fmaf(v.x, a[qi][0], b[qi][0]);
-        float y1 = fmaf(v.y, a[qi][1], b[qi][1]);
-        float y2 = fmaf(v.z, a[qi][2], b[qi][2]);
-        float y3 = fmaf(v.w, a[qi][3], b[qi][3]);
-        if (apply_silu) {
-          y0 = silu_f(y0);
-          y1 = silu_f(y1);
-          y2 = silu_f(y2);
-          y3 = silu_f(y3);
-        }
-        uint2 u = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-        *reinterpret_cast<uint2*>(out + row * C + c) = u;
-        if (raw_out != nullptr) {
-          uint2 w = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-          *reinterpret_cast<uint2*>(raw_out + row * C + c) = w;
-        }
-      }
+  const size_t img_row = static_cast<size_t>(n) * hw;
+  auto emit = [&](size_t row, int qi, const float4& v) {
+    const int c = (tx + qi * TX) * 4;
+    float y0 = fmaf(v.x, a[qi][0], b[qi][0]);
+    float y1 = fmaf(v.y, a[qi][1], b[qi][1]);
+    float y2 = fmaf(v.z, a[qi][2], b[qi][2]);
+    float y3 = fmaf(v.w, a[qi][3], b[qi][3]);
+    if (apply_silu) {
+      y0 = silu_f(y0);
+      y1 = silu_f(y1);
+      y2 = silu_f(y2);
+      y3 = silu_f(y3);
     }
+    *reinterpret_cast<uint2*>(out + row * C + c) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    if (raw_out != nullptr)
+      *reinterpret_cast<uint2*>(raw_out + row * C + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  };
+  int r = r0 + ty;
+  for (; r + (UNROLL - 1) * TY < r1; r += UNROLL * TY) {
+    float4 v[UNROLL][NQI];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int qi = 0; qi < NQI; ++qi) emit(img_row + r + u * TY, qi, v[u][qi]);
+  }
+  for (; r < r1; r += TY) {
+#pragma unroll
+    for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4));
   }
 }
 
-constexpr int LN_MAX_Q = 16;  // C <= 4 * 32 * 16 = 2048
-
-// one warp per row; the row lives in registers between the two passes
-__global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
+// ---- LayerNorm: one warp per row; the row lives in registers between the two passes --------------
+template <int NQ>  // quads per lane: C <= 128 * NQ
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int quads = C >> 2;
   const float* xr = x + static_cast<size_t>(row) * C;
-  float4 v[LN_MAX_Q];
+  float4 v[NQ];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_Q; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qd = i * 32 + lane;
-    if (qd < quads) {
-      v[i] = __ldg(reinterpret_cast<const float4*>(xr) + qd);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+    if (qd < quads) v[i] = __ldg(reinterpret_cast<const float4*>(xr) + qd);
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = i * 32 + lane;
+    if (qd < quads) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_Q; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qd = i * 32 + lane;
     if (qd < quads) {
       const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
@@ -216,7 +266,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, cons
   const float rstd = rsqrtf(q / C + eps);
   bf16* orow = out + static_cast<size_t>(row) * C;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_Q; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qd = i * 32 + lane;
     if (qd < quads) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + qd);
@@ -228,6 +278,22 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, cons
       *reinterpret_cast<uint2*>(orow + qd * 4) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
     }
   }
+}
+
+template <int NQI>
+cudaError_t launch_gn_t(const GnGeom& g, const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
+                        const float* gamma, const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out,
+                        float* partial, cudaStream_t stream) {
+  constexpr int UNROLL = (NQI >= 4) ? 2 : 4;
+  const int C = C1 + C2;
+  dim3 grid(g.n_chunks, n_img), block(g.TX, g.TY);
+  gn_stats_kernel<NQI, UNROLL><<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(
+      x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  gn_apply_kernel<NQI, UNROLL><<<grid, block, 0, stream>>>(x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, g.n_chunks,
+                                                           partial, gamma, beta, eps, apply_silu, out, raw_out);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -249,24 +315,29 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
     set_error("groupnorm: too many channels for this kernel");
     return cudaErrorInvalidValue;
   }
-  dim3 grid(g.n_chunks, n_img), block(g.TX, g.TY);
-  gn_stats_kernel<<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(x1, x2, C1, C2, hw, g.nqi, g.cpg,
-                                                                  g.rows_per_chunk, partial);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  gn_apply_kernel<<<grid, block, 0, stream>>>(x1, x2, C1, C2, hw, g.nqi, g.cpg, g.rows_per_chunk, g.n_chunks,
-                                              partial, gamma, beta, eps, apply_silu, out, raw_out);
-  return cudaGetLastError();
+#define CAP4D_GN_CASE(N) \
+  return launch_gn_t<N>(g, x1, C1, x2, C2, n_img, hw, gamma, beta, eps, apply_silu, out, raw_out, partial, stream)
+  if (g.nqi == 1) CAP4D_GN_CASE(1);
+  if (g.nqi == 2) CAP4D_GN_CASE(2);
+  CAP4D_GN_CASE(4);
+#undef CAP4D_GN_CASE
 }
 
 cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
                              bf16* out, cudaStream_t stream) {
-  if (C % 4 != 0 || C > 4 * 32 * LN_MAX_Q) {
+  if (C % 4 != 0 || C > 4 * 32 * 16) {
     set_error("layernorm: C must be a multiple of 4 and <= 2048");
     return cudaErrorInvalidValue;
   }
   const int warps = 8;
-  layernorm_kernel<<<(M + warps - 1) / warps, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+  const int grid = (M + warps - 1) / warps;
+  const int quads = C / 4;
+  if (quads <= 32 * 4)
+    layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+  else if (quads <= 32 * 8)
+    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+  else
+    layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
   return cudaGetLastError();
 }
 

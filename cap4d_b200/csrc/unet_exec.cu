@@ -1327,6 +1327,18 @@ int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, 
   return run_timed([&](cudaStream_t s) { return launch_attn(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
 }
 
+int cap4d_b200_attention_trace(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,
+                               long long* trace) {
+  AttnPlan p;
+  if (!make_attn_plan(&p, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), M, C, L, scale)) return 10;
+  cudaError_t e = launch_attn(p, static_cast<cudaStream_t>(stream), trace);
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    return 8;
+  }
+  return 0;
+}
+
 int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
                               const float* gamma, const float* beta, float eps, int apply_silu, uint16_t* out,
                               uint16_t* raw_out, void* stream, float* ms_out, int iters) {

@@ -118,6 +118,11 @@ int cap4d_b200_conv3x3_bf16(const uint16_t* A, const uint16_t* Wt, int n_img, in
 int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,
                               float* ms_out, int iters);
 
+/* Instrumented attention launch: device buffer trace[3][16][8] (int64) receives clock64() stamps of
+ * CTA (0,0,0) for the first 16 KV tiles: rows 0/1 = softmax warpgroups, row 2 = MMA issuer. */
+int cap4d_b200_attention_trace(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,
+                               long long* trace);
+
 /* GroupNorm32(32, C1+C2)(cat([x1, x2], channel)) (+SiLU) on NHWC fp32 -> bf16; x2 may be NULL. */
 int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
                               const float* gamma, const float* beta, float eps, int apply_silu, uint16_t* out,

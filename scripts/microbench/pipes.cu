@@ -1,0 +1,60 @@
+// Pipe-throughput micro-benchmarks for B200 (sm_100a): how many cycles does an SMSP need per
+// warp-instruction of MUFU.EX2 / FFMA / FMNMX, alone and mixed?  One CTA per SM, W warps per CTA.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu && ./pipes
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int MODE>
+__global__ void k(float* out, int iters, long long* cyc) {
+  float a[16];
+  for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  float s = 0.f, m = -1e30f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (MODE == 0) a[i] = ex2(a[i]);                                  // MUFU only
+      if (MODE == 1) a[i] = fmaf(a[i], 1.0001f, 0.5f);                  // FFMA only
+      if (MODE == 2) m = fmaxf(m, a[i]), a[i] = m * 0.5f;               // dependent; ignore
+      if (MODE == 3) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; a[i] = e; }  // softmax inner loop
+      if (MODE == 4) { asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(s)); }  // FMNMX only
+      if (MODE == 6) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(a[i]), "f"(s)); a[i] = __uint_as_float(u | 0x3f000000u); }
+      if (MODE == 7) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; if (i & 1) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(e), "f"(a[i-1])); m += __uint_as_float(u); } a[i] = e; }
+      if (MODE == 5) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; a[i] = e; asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(e)); }
+    }
+  }
+  long long t1 = clock64();
+  float r = s + m;
+  for (int i = 0; i < 16; ++i) r += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+template <int MODE>
+void run(const char* name, int warps) {
+  float* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 8);
+  int iters = 4096;
+  k<MODE><<<148, warps * 32>>>(out, iters, cyc);
+  k<MODE><<<148, warps * 32>>>(out, iters, cyc);
+  cudaDeviceSynchronize();
+  long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+  double per_smsp_warp_instr = (double)c / ((double)iters * 16 * (warps / 4.0));
+  printf("%-28s warps/SM %2d: %.2f cycles per (loop element) per SMSP-warp\n", name, warps, per_smsp_warp_instr);
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  for (int w : {4, 8, 16}) {
+    run<0>("MUFU.EX2", w);
+    run<1>("FFMA", w);
+    run<4>("FMNMX", w);
+    run<3>("FFMA+EX2+FADD", w);
+    run<5>("FFMA+EX2+FADD+FMNMX", w);
+    run<6>("F2FP.BF16x2", w);
+    run<7>("FFMA+EX2+FADD+F2FP/2", w);
+  }
+  return 0;
+}
