@@ -13,11 +13,13 @@
 //   * an optional second plain A segment appends K (the ResBlock's 1x1 skip conv is accumulated
 //     into the same TMEM tile as its second 3x3 conv).
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
-// smem ring of `stages` {A 128x64, B BNx64} bf16 tiles (128B swizzle); two TMEM accumulator
-// stages (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-9 epilogue.
+// CTA tile (msub*128) x BN; smem ring of `stages` {A msub x 128x64, B BNx64} bf16 tiles (128B swizzle);
+// two TMEM accumulator stages when they fit (msub*BN <= 256) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -27,13 +29,12 @@ namespace cap4d {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;                     // rows of one UMMA (TMEM lanes)
 constexpr int BK = 64;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int A_SUB_BYTES = BM * BK * 2;    // 16 KiB: one 128-row A sub-tile
 constexpr int MAX_STAGES = 8;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator stages
 
 struct SmemTail {
   uint64_t full[MAX_STAGES];
@@ -43,50 +44,62 @@ struct SmemTail {
   uint32_t tmem_base;
 };
 
+// 256-bit global accesses (sm_100): a thread owns a whole accumulator row, so its 32 columns are 4
+// (fp32) or 2 (bf16) 32-byte pieces of ONE 128 B line; wider pieces halve the number of L1 wavefronts the
+// row-per-thread pattern costs.
+__device__ __forceinline__ void st_global_v8(void* dst, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* src, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(src));
+}
+
 __device__ __forceinline__ void epilogue_store_f32(float* dst, const float* acc) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-  }
+  for (int j = 0; j < 32; j += 8) st_global_v8(dst + j, reinterpret_cast<const uint32_t*>(acc + j));
 }
 
 __device__ __forceinline__ void epilogue_store_bf16(bf16* dst, const float* acc) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 u;
-    u.x = pack_bf16x2(acc[j], acc[j + 1]);
-    u.y = pack_bf16x2(acc[j + 2], acc[j + 3]);
-    u.z = pack_bf16x2(acc[j + 4], acc[j + 5]);
-    u.w = pack_bf16x2(acc[j + 6], acc[j + 7]);
-    *reinterpret_cast<uint4*>(dst + j) = u;
+  for (int j = 0; j < 32; j += 16) {
+    uint32_t u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = pack_bf16x2(acc[j + 2 * i], acc[j + 2 * i + 1]);
+    st_global_v8(dst + j, u);
   }
 }
 
 __device__ __forceinline__ void add_vec32(float* acc, const float* __restrict__ src) {
+  float b[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float4 b = __ldg(reinterpret_cast<const float4*>(src + j));
-    acc[j] += b.x;
-    acc[j + 1] += b.y;
-    acc[j + 2] += b.z;
-    acc[j + 3] += b.w;
-  }
+  for (int j = 0; j < 32; j += 8) ld_global_nc_v8(src + j, b + j);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] += b[j];
 }
 
+// A CTA tile is (msub * 128) x BN: msub in {1, 2} 128-row sub-tiles share one B (weight) tile per k-block,
+// which raises the FLOPs per byte streamed from L2 - the resource this kernel is bound by - from
+// 2*128*BN*64 / (16K + 128 BN) to 2*256*BN*64 / (32K + 128 BN).
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage_bytes = p.msub * A_SUB_BYTES;
   const int b_stage_bytes = p.BN * BK * 2;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * A_STAGE_BYTES;
+  uint8_t* sB = smem + p.stages * a_stage_bytes;
   SmemTail* tail = reinterpret_cast<SmemTail*>(sB + p.stages * b_stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  const int acc_stride = (p.n_acc == 2) ? (TMEM_COLS / 2) : 0;  // TMEM columns between accumulator stages
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -98,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tail->tmem_full[a], 1);
-      mbar_init(&tail->tmem_empty[a], 128);
+      mbar_init(&tail->tmem_empty[a], 256);
     }
     fence_mbar_init();
   }
@@ -116,34 +129,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+      const uint32_t tx_bytes = a_stage_bytes + b_stage_bytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.tiles_n;
         const int n_tile = tile - m_tile * p.tiles_n;
-        int n0 = 0, y0 = 0;
-        if (p.a_conv) {
-          const int pix0 = m_tile * BM;
-          const int hw = p.H * p.W;
-          n0 = pix0 / hw;
-          y0 = (pix0 - n0 * hw) / p.W;
+        // per-tile coordinates of the (up to two) 128-row sub-tiles; nothing in the k loop divides
+        int row0[2], n0[2], y0[2];
+        for (int sub = 0; sub < 2; ++sub) {
+          row0[sub] = (m_tile * p.msub + sub) * BM;  // first output row (pixel) of the sub-tile
+          n0[sub] = y0[sub] = 0;
+          if (p.a_conv) {
+            const int hw = p.H * p.W;
+            n0[sub] = row0[sub] / hw;
+            y0[sub] = (row0[sub] - n0[sub] * hw) / p.W;
+          }
         }
+        const int b_row = n_tile * p.BN;
+        int tap = 0, c0 = 0;  // conv: filter tap and channel offset of the current k-block
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
-          void* dstA = sA + stage * A_STAGE_BYTES;
+          uint8_t* dstA = sA + stage * a_stage_bytes;
           if (kb < p.seg0_kb) {
             if (p.a_conv) {
-              const int tap = kb / p.cin_kb;
-              const int c0 = (kb - tap * p.cin_kb) * BK;
-              tma_load_4d(dstA, &tmA, &tail->full[stage], c0, p.tap_dx[tap], y0 + p.tap_dy[tap],
-                          n0 + p.tap_dn[tap]);
+              const int dx = p.tap_dx[tap], dy = p.tap_dy[tap], dn = p.tap_dn[tap];
+              tma_load_4d(dstA, &tmA, &tail->full[stage], c0, dx, y0[0] + dy, n0[0] + dn);
+              if (p.msub == 2) tma_load_4d(dstA + A_SUB_BYTES, &tmA, &tail->full[stage], c0, dx, y0[1] + dy, n0[1] + dn);
+              c0 += BK;
+              if (c0 == p.cin_kb * BK) {
+                c0 = 0;
+                ++tap;
+              }
             } else {
-              tma_load_2d(dstA, &tmA, &tail->full[stage], kb * BK, m_tile * BM);
+              tma_load_2d(dstA, &tmA, &tail->full[stage], kb * BK, row0[0]);
+              if (p.msub == 2) tma_load_2d(dstA + A_SUB_BYTES, &tmA, &tail->full[stage], kb * BK, row0[1]);
             }
           } else {
-            tma_load_2d(dstA, &tmA2, &tail->full[stage], (kb - p.seg0_kb) * BK, m_tile * BM);
+            tma_load_2d(dstA, &tmA2, &tail->full[stage], (kb - p.seg0_kb) * BK, row0[0]);
+            if (p.msub == 2) tma_load_2d(dstA + A_SUB_BYTES, &tmA2, &tail->full[stage], (kb - p.seg0_kb) * BK, row0[1]);
           }
-          tma_load_2d(sB + stage * b_stage_bytes, &tmB, &tail->full[stage], kb * BK, n_tile * p.BN);
+          tma_load_2d(sB + stage * b_stage_bytes, &tmB, &tail->full[stage], kb * BK, b_row);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -155,24 +180,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BM, p.BN, 0);
+      const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(sA));  // stage / sub-tile / k offsets are added
+      const uint64_t bdesc0 = umma_smem_desc_sw128(smem_u32(sB));  // to the 14-bit (>>4) address field
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = (p.n_acc == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * a_stage_bytes) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (p.msub == 2) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem + p.BN, adesc + (A_SUB_BYTES >> 4) + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&tail->empty[stage]);
           if (++stage == p.stages) {
@@ -184,59 +216,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Thread <-> accumulator row (TMEM lane); two warps share each TMEM lane quarter and split the
+    // tile's column chunks, so every SM sub-partition has two epilogue warps to hide the
+    // tcgen05.ld / global-load latencies.  Each thread reads / writes whole 128 B (fp32) or 64 B (bf16)
+    // row segments; the next chunk's tcgen05.ld is in flight while the current one is written out.
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the chunks this warp handles
+    const bool geglu = (p.out_mode & 15) == OUT_GEGLU_BF16;
+    const bool dbg_noepi = (p.out_mode & 32) != 0;
+    const int tcols = geglu ? 64 : 32;         // TMEM columns per chunk
+    const int cps = p.BN / tcols;              // chunks per sub-tile
+    const int nchunks = p.msub * cps;
+    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
+    const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.tiles_n;
       const int n_tile = tile - m_tile * p.tiles_n;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = (p.n_acc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE;
-      const float* rb = nullptr;
-      if (p.rowbias != nullptr && row_ok) rb = p.rowbias + static_cast<size_t>(row / p.rowbias_div) * p.rowbias_ld;
-      const float* res = nullptr;
-      if (p.residual != nullptr && row_ok) res = p.residual + static_cast<size_t>(row) * p.ldr;
-
-      if (p.out_mode == OUT_GEGLU_BF16) {
-        // weight rows are interleaved in blocks of 32: [x(32) | gate(32)] -> out 32 columns
-        const int npairs = p.BN / 64;
-        for (int c = 0; c < npairs; ++c) {
-          uint32_t vx[32], vg[32];
-          tmem_ld32(taddr + c * 64, vx);
-          tmem_ld32(taddr + c * 64 + 32, vg);
-          tmem_ld_wait();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
+      auto chunk_col = [&](int cc) { return (cc / cps) * p.BN + (cc % cps) * tcols; };  // TMEM column of chunk cc
+      uint32_t v[32], vg[32];
+      if (c_begin < c_end) {
+        tmem_ld32(taddr + chunk_col(c_begin), v);
+        if (geglu) tmem_ld32(taddr + chunk_col(c_begin) + 32, vg);
+      }
+      for (int cc = c_begin; cc < c_end; ++cc) {
+        const int sub = cc / cps, c = cc - sub * cps;
+        const int row = (m_tile * p.msub + sub) * BM + q * 32 + lane;
+        const bool row_ok = row < p.M && !dbg_noepi;
+        tmem_ld_wait();
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+        if (geglu) {
+          // weight rows are interleaved in blocks of 32: [x(32) | gate(32)] -> 32 output columns
+          float ag[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ag[j] = __uint_as_float(vg[j]);
+          if (cc + 1 < c_end) {
+            tmem_ld32(taddr + chunk_col(cc + 1), v);
+            tmem_ld32(taddr + chunk_col(cc + 1) + 32, vg);
+          }
           if (row_ok) {
-            float* ax = reinterpret_cast<float*>(vx);
-            float* ag = reinterpret_cast<float*>(vg);
             const int col0 = n_tile * p.BN + c * 64;
             if (p.bias != nullptr) {
-              add_vec32(ax, p.bias + col0);
+              add_vec32(a, p.bias + col0);
               add_vec32(ag, p.bias + col0 + 32);
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ax[j] = ax[j] * gelu_erf_f(ag[j]);
-            bf16* dst = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col0 >> 1);
-            epilogue_store_bf16(dst, ax);
+            for (int j = 0; j < 32; ++j) a[j] = a[j] * gelu_erf_f(ag[j]);
+            epilogue_store_bf16(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col0 >> 1), a);
           }
-        }
-      } else {
-        const int nchunks = p.BN / 32;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
+        } else {
+          if (cc + 1 < c_end) tmem_ld32(taddr + chunk_col(cc + 1), v);
           if (row_ok) {
-            float* a = reinterpret_cast<float*>(v);
             const int col0 = n_tile * p.BN + c * 32;
+            if (p.residual != nullptr) add_vec32(a, p.residual + static_cast<size_t>(row) * p.ldr + col0);
+            if (p.rowbias != nullptr)
+              add_vec32(a, p.rowbias + static_cast<size_t>(row / p.rowbias_div) * p.rowbias_ld + col0);
             if (p.bias != nullptr) add_vec32(a, p.bias + col0);
-            if (rb != nullptr) add_vec32(a, rb + col0);
-            if (res != nullptr) add_vec32(a, res + col0);
-            if (p.out_mode == OUT_F32) {
+            if ((p.out_mode & 15) == OUT_F32) {
               epilogue_store_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
             } else {
               epilogue_store_bf16(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
@@ -320,24 +364,44 @@ int sm_count() {
 
 namespace {
 
-int pick_bn(int M, int N, bool geglu) {
+struct TileCfg {
+  int msub, bn, n_acc;
+};
+
+// Pick (msub, BN).  Measured on B200 (scripts/bench_shapes.py, profiles/): the main loop of this
+// kernel is bound by SHARED-MEMORY bandwidth (128 B/clk/SM), not by L2 or the tensor pipe: per
+// k-block the TMA writes msub*16 KiB (A) + BN*128 B (B) into smem and the UMMAs read msub*16 KiB (A)
+// + msub*BN*128 B (B is re-read by every 128-row sub-tile).  Cost = waves * k-blocks *
+// max(tensor cycles, smem bytes / 128) + the epilogue where it cannot overlap (single TMEM stage).
+TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
-  const int tiles_m = (M + BM - 1) / BM;
   const int sms = sm_count();
-  int best = 0;
+  TileCfg best{0, 0, 0};
+  if (const char* f = getenv("CAP4D_GEMM_FORCE")) {  // "msub,bn" for experiments
+    int ms = 0, bn = 0;
+    if (sscanf(f, "%d,%d", &ms, &bn) == 2 && (ms == 1 || ms == 2) && bn > 0 && N % bn == 0 && bn % 32 == 0 &&
+        bn <= 256 && (!geglu || bn % 64 == 0))
+      return TileCfg{ms, bn, (ms * bn <= 256) ? 2 : 1};
+  }
   double best_cost = 1e30;
-  for (int bn : cands) {
-    if (N % bn != 0) continue;
-    if (geglu && (bn % 64 != 0)) continue;
-    const long tiles = static_cast<long>(tiles_m) * (N / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    // per-tile main-loop time ~ bn (MMA cycles per k-step); small tiles pay a fixed cost and are
-    // shared-memory-bandwidth bound (A tile re-read per N tile)
-    const double per_tile = std::max(bn, 128) + 40.0;
-    const double cost = waves * per_tile;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
+  for (int msub = 1; msub <= 2; ++msub) {
+    const int tiles_m = (M + msub * BM - 1) / (msub * BM);
+    for (int bn : cands) {
+      if (N % bn != 0) continue;
+      if (geglu && (bn % 64 != 0)) continue;
+      const int n_acc = (msub * bn <= 256) ? 2 : 1;
+      const long tiles = static_cast<long>(tiles_m) * (N / bn);
+      const long waves = (tiles + sms - 1) / sms;
+      const double mma = 2.0 * msub * bn;
+      const double smem = (2.0 * msub * 16384.0 + (1.0 + msub) * bn * 128.0) / 128.0;
+      const double epi = 8.0 * msub * bn;  // cycles to drain one tile's accumulator (8 epilogue warps)
+      double per_tile = num_kb * std::max(mma, smem) + 600.0;
+      per_tile = (n_acc == 2) ? std::max(per_tile, epi) : per_tile + epi;
+      const double cost = waves * per_tile;
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        best = TileCfg{msub, bn, n_acc};
+      }
     }
   }
   return best;
@@ -351,17 +415,20 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
     set_error("gemm: K must be a multiple of 64");
     return false;
   }
-  const int bn = pick_bn(p.M, N, out_mode == OUT_GEGLU_BF16);
-  if (bn == 0) {
+  const TileCfg cfg = pick_tile(p.M, N, Ktot / BK, (out_mode & 15) == OUT_GEGLU_BF16);
+  if (cfg.bn == 0) {
     set_error("gemm: N must be a multiple of 32 (64 for GEGLU)");
     return false;
   }
+  const int bn = cfg.bn;
   p.N = N;
   p.BN = bn;
-  p.tiles_m = (p.M + BM - 1) / BM;
+  p.msub = cfg.msub;
+  p.n_acc = cfg.n_acc;
+  p.tiles_m = (p.M + cfg.msub * BM - 1) / (cfg.msub * BM);
   p.tiles_n = N / bn;
   p.num_kb = Ktot / BK;
-  const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  const int stage_bytes = cfg.msub * A_SUB_BYTES + bn * BK * 2;
   int stages = (220 * 1024 - static_cast<int>(sizeof(SmemTail)) - 1024) / stage_bytes;
   stages = std::min(stages, MAX_STAGES);
   stages = std::min(stages, std::max(2, p.num_kb));
@@ -376,8 +443,7 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
   p.rowbias_ld = rowbias_ld;
   p.residual = residual;
   p.ldr = ldr;
-  const int total = p.tiles_m * p.tiles_n;
-  plan->grid = std::min(total, sm_count());
+  plan->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
   plan->flops = 2.0 * p.M * static_cast<double>(N) * Ktot;
   // weights: [N][Ktot] row-major
   uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};

@@ -31,6 +31,8 @@ enum GemmOutMode { OUT_F32 = 0, OUT_BF16 = 1, OUT_GEGLU_BF16 = 2 };
 struct GemmParams {
   int M, N;          // logical output size (GEGLU: N counts the interleaved x|gate columns)
   int BN;            // N tile, multiple of 32, <= 256
+  int msub;          // 128-row sub-tiles per CTA tile (1 or 2)
+  int n_acc;         // TMEM accumulator stages (2 if msub*BN <= 256)
   int tiles_m, tiles_n;
   int num_kb;        // K / 64 over all segments
   int seg0_kb;       // k-blocks served by A (taps * cin_kb for conv); the rest come from A2
