@@ -108,12 +108,13 @@ cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* tr
 // GroupNorm(32 groups) over NHWC fp32, optionally over the channel
 // concatenation of two tensors (C1 from x1, C2 from x2); writes bf16
 // [M][C1+C2] = (silu?)(gn(x)) and optionally a raw bf16 copy of x.
-// partial: scratch fp32 [n_img][GN_MAX_CHUNKS][32][2].
+// partial: scratch of groupnorm_partial_bytes(n_img): fp32 [n_img][GN_MAX_CHUNKS][32][2] + barrier counters.
 enum { GN_MAX_CHUNKS = 64 };
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
                              cudaStream_t stream);
 size_t groupnorm_partial_bytes(int n_img);
+size_t groupnorm_sync_offset(int n_img);  // the bytes from here to the end must be zero before the first launch
 
 // LayerNorm over the last dim of fp32 [M][C] -> bf16 [M][C]
 cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,

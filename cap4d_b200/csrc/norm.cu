@@ -62,59 +62,79 @@ __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const fl
   return __ldg(reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1)));
 }
 
-// ---- GroupNorm statistics -------------------------------------------------------------------
-// grid (n_chunks, n_img), block (TX, TY): thread (tx, ty) owns channel quads tx + i*TX (i < NQI) and
-// rows ty, ty+TY, ... of its chunk, UNROLL rows (= UNROLL*NQI independent 16 B loads) per iteration.
+// ---- GroupNorm (+SiLU), one kernel ---------------------------------------------------------------
+// grid (n_chunks, n_img) = image-major block order, block (TX, TY): thread (tx, ty) owns channel quads
+// tx + i*TX (i < NQI) and rows ty, ty+TY, ... of its chunk, UNROLL rows (= UNROLL*NQI independent 16 B
+// loads) per iteration.
+//   phase 1  per-chunk (sum, sumsq) of the 32 groups -> partial[n][chunk][g][2] (fixed order: deterministic)
+//   barrier  the chunks of ONE image wait for each other on a global counter.  Blocks are dispatched in
+//            linear order, so every block an image waits for is already resident or ahead of it in the
+//            queue, and the blocks of earlier images can always finish: no deadlock.
+//   phase 2  reduce the partials, normalise the same rows again - they were read a few microseconds ago
+//            and come from L2 (the working set is the handful of images in flight, not the whole tensor),
+//            so HBM sees 4 B in + 2 B out per element instead of 8 + 2.
+struct GnSync {
+  unsigned int arrived, done;
+};
+
 template <int NQI, int UNROLL>
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
-                int rows_per_chunk, float* __restrict__ partial) {
+gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
+                int rows_per_chunk, int n_chunks, float* __restrict__ partial, GnSync* __restrict__ sync,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int apply_silu,
+                bf16* __restrict__ out, bf16* __restrict__ raw_out) {
   extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
+  __shared__ double s_part[8][GN_GROUPS][2];
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   const int C = C1 + C2;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  const int tid = ty * TX + tx;
+  const int tid = ty * TX + tx, nthreads = TX * TY;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
-  float sum[NQI][4], sq[NQI][4];
-#pragma unroll
-  for (int qi = 0; qi < NQI; ++qi)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sum[qi][k] = sq[qi][k] = 0.f;
   const size_t img_row = static_cast<size_t>(n) * hw;
-  int r = r0 + ty;
-  for (; r + (UNROLL - 1) * TY < r1; r += UNROLL * TY) {
-    float4 v[UNROLL][NQI];
+
+  // ---------------- phase 1: statistics of this chunk ----------------
+  {
+    float sum[NQI][4], sq[NQI][4];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    for (int qi = 0; qi < NQI; ++qi)
 #pragma unroll
-      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+      for (int k = 0; k < 4; ++k) sum[qi][k] = sq[qi][k] = 0.f;
+    int r = r0 + ty;
+    for (; r + (UNROLL - 1) * TY < r1; r += UNROLL * TY) {
+      float4 v[UNROLL][NQI];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int qi = 0; qi < NQI; ++qi) {
+          sum[qi][0] += v[u][qi].x; sq[qi][0] = fmaf(v[u][qi].x, v[u][qi].x, sq[qi][0]);
+          sum[qi][1] += v[u][qi].y; sq[qi][1] = fmaf(v[u][qi].y, v[u][qi].y, sq[qi][1]);
+          sum[qi][2] += v[u][qi].z; sq[qi][2] = fmaf(v[u][qi].z, v[u][qi].z, sq[qi][2]);
+          sum[qi][3] += v[u][qi].w; sq[qi][3] = fmaf(v[u][qi].w, v[u][qi].w, sq[qi][3]);
+        }
+    }
+    for (; r < r1; r += TY) {
 #pragma unroll
       for (int qi = 0; qi < NQI; ++qi) {
-        sum[qi][0] += v[u][qi].x; sq[qi][0] = fmaf(v[u][qi].x, v[u][qi].x, sq[qi][0]);
-        sum[qi][1] += v[u][qi].y; sq[qi][1] = fmaf(v[u][qi].y, v[u][qi].y, sq[qi][1]);
-        sum[qi][2] += v[u][qi].z; sq[qi][2] = fmaf(v[u][qi].z, v[u][qi].z, sq[qi][2]);
-        sum[qi][3] += v[u][qi].w; sq[qi][3] = fmaf(v[u][qi].w, v[u][qi].w, sq[qi][3]);
+        const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4);
+        sum[qi][0] += v.x; sq[qi][0] = fmaf(v.x, v.x, sq[qi][0]);
+        sum[qi][1] += v.y; sq[qi][1] = fmaf(v.y, v.y, sq[qi][1]);
+        sum[qi][2] += v.z; sq[qi][2] = fmaf(v.z, v.z, sq[qi][2]);
+        sum[qi][3] += v.w; sq[qi][3] = fmaf(v.w, v.w, sq[qi][3]);
       }
-  }
-  for (; r < r1; r += TY) {
+    }
+    float* my = s_ch + static_cast<size_t>(ty) * 2 * C;
 #pragma unroll
     for (int qi = 0; qi < NQI; ++qi) {
-      const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4);
-      sum[qi][0] += v.x; sq[qi][0] = fmaf(v.x, v.x, sq[qi][0]);
-      sum[qi][1] += v.y; sq[qi][1] = fmaf(v.y, v.y, sq[qi][1]);
-      sum[qi][2] += v.z; sq[qi][2] = fmaf(v.z, v.z, sq[qi][2]);
-      sum[qi][3] += v.w; sq[qi][3] = fmaf(v.w, v.w, sq[qi][3]);
+      const int c = (tx + qi * TX) * 4;
+      *reinterpret_cast<float4*>(my + c) = make_float4(sum[qi][0], sum[qi][1], sum[qi][2], sum[qi][3]);
+      *reinterpret_cast<float4*>(my + C + c) = make_float4(sq[qi][0], sq[qi][1], sq[qi][2], sq[qi][3]);
     }
-  }
-  float* my = s_ch + static_cast<size_t>(ty) * 2 * C;
-#pragma unroll
-  for (int qi = 0; qi < NQI; ++qi) {
-    const int c = (tx + qi * TX) * 4;
-    *reinterpret_cast<float4*>(my + c) = make_float4(sum[qi][0], sum[qi][1], sum[qi][2], sum[qi][3]);
-    *reinterpret_cast<float4*>(my + C + c) = make_float4(sq[qi][0], sq[qi][1], sq[qi][2], sq[qi][3]);
   }
   __syncthreads();
   if (tid < GN_GROUPS) {
@@ -127,33 +147,32 @@ gn_stats_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
       }
     }
     float* dst = partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + chunk) * GN_GROUPS + tid) * 2;
-    dst[0] = s;
-    dst[1] = q;
+    __stcg(reinterpret_cast<float2*>(dst), make_float2(s, q));
+    __threadfence();
   }
-}
+  __syncthreads();
 
-// ---- GroupNorm apply (+SiLU) ------------------------------------------------------------------
-template <int NQI, int UNROLL>
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
-                int rows_per_chunk, int n_chunks, const float* __restrict__ partial,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int apply_silu,
-                bf16* __restrict__ out, bf16* __restrict__ raw_out) {
-  __shared__ double s_part[8][GN_GROUPS][2];
-  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
-  const int C = C1 + C2;
-  const int n = blockIdx.y, chunk = blockIdx.x;
-  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  const int tid = ty * TX + tx, nthreads = TX * TY;
-  // fixed-order reduction of the per-chunk partials, spread over up to 8 warps: deterministic
+  // ---------------- barrier over the chunks of image n ----------------
+  if (tid == 0) {
+    atomicAdd(&sync[n].arrived, 1u);
+    long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&sync[n].arrived) : "memory");
+      if (seen < static_cast<unsigned int>(n_chunks) && clock64() - t0 > CAP4D_WATCHDOG_CYCLES) __trap();
+    } while (seen < static_cast<unsigned int>(n_chunks));
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: statistics of the image, then normalise ----------------
   const int nparts = min(8, max(1, nthreads / 32));
   {
     const int part = tid >> 5, g = tid & 31;
     if (part < nparts) {
       double s = 0.0, q = 0.0;
       for (int ch = part; ch < n_chunks; ch += nparts) {
-        const float2 v =
-            *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + ch) * GN_GROUPS + g) * 2);
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(
+            partial + ((static_cast<size_t>(n) * GN_MAX_CHUNKS + ch) * GN_GROUPS + g) * 2));
         s += v.x;
         q += v.y;
       }
@@ -189,9 +208,6 @@ gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
       b[qi][k] = be - s_mean[g] * s_rstd[g] * ga;
     }
   }
-  const int r0 = chunk * rows_per_chunk;
-  const int r1 = min(hw, r0 + rows_per_chunk);
-  const size_t img_row = static_cast<size_t>(n) * hw;
   auto emit = [&](size_t row, int qi, const float4& v) {
     const int c = (tx + qi * TX) * 4;
     float y0 = fmaf(v.x, a[qi][0], b[qi][0]);
@@ -223,6 +239,16 @@ gn_apply_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
   for (; r < r1; r += TY) {
 #pragma unroll
     for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4));
+  }
+  // ---------------- the last chunk of the image resets its counters for the next launch ----------------
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int old = atomicAdd(&sync[n].done, 1u);
+    if (old == static_cast<unsigned int>(n_chunks) - 1u) {
+      sync[n].arrived = 0u;
+      sync[n].done = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -287,20 +313,21 @@ cudaError_t launch_gn_t(const GnGeom& g, const float* x1, int C1, const float* x
   constexpr int UNROLL = (NQI >= 4) ? 2 : 4;
   const int C = C1 + C2;
   dim3 grid(g.n_chunks, n_img), block(g.TX, g.TY);
-  gn_stats_kernel<NQI, UNROLL><<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(
-      x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, partial);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  gn_apply_kernel<NQI, UNROLL><<<grid, block, 0, stream>>>(x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, g.n_chunks,
-                                                           partial, gamma, beta, eps, apply_silu, out, raw_out);
+  GnSync* sync = reinterpret_cast<GnSync*>(partial + static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2);
+  gn_fused_kernel<NQI, UNROLL><<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(
+      x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, g.n_chunks, partial, sync, gamma, beta, eps, apply_silu, out,
+      raw_out);
   return cudaGetLastError();
 }
 
 }  // namespace
 
+// per-chunk partials followed by the per-image barrier counters (which must start zeroed, see
+// groupnorm_sync_offset; the kernel leaves them zeroed again)
 size_t groupnorm_partial_bytes(int n_img) {
-  return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float);
+  return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float) + static_cast<size_t>(n_img) * 8;
 }
+size_t groupnorm_sync_offset(int n_img) { return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float); }
 
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,

@@ -130,6 +130,28 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
+// TMA store (smem tile -> global, bulk async group); OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups are still READING their smem source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------
@@ -274,22 +296,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU (tanh.approx, |err| ~ 2^-11) instead of ex2 + rcp; the
+// result is rounded to bf16 (2^-9) right after.
+__device__ __forceinline__ float silu_f(float x) {
+  float t;
+  const float hx = 0.5f * x;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
+}
 
-// erf GELU (torch.nn.functional.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
-// far below the bf16 rounding of the result): one MUFU.RCP, one MUFU.EX2 and a handful of FMAs
-// instead of erff's ~30 instructions - the GEGLU epilogue is ALU-bound otherwise.
+// erf GELU (torch.nn.functional.gelu default).  erf(z) = z * P(z^2) on |z| <= 3 (degree-8 minimax fit,
+// |error| <= 4e-5, erf saturates to 1 beyond; two orders of magnitude below the bf16 rounding of the
+// result): FMA-pipe only - the GEGLU epilogue is instruction-bound and MUFU runs at 1/8 the FMA rate.
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * __expf(-z * z);  // 1 - erf(z)
-  const float erf_abs = 1.0f - e;
-  const float erf_x = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_x);
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 3.0f);
+  const float t = z * z;
+  float p = 4.918275920e-08f;
+  p = fmaf(p, t, -2.267730679e-06f);
+  p = fmaf(p, t, 4.614729187e-05f);
+  p = fmaf(p, t, -5.535572418e-04f);
+  p = fmaf(p, t, 4.437862430e-03f);
+  p = fmaf(p, t, -2.564961277e-02f);
+  p = fmaf(p, t, 1.118625030e-01f);
+  p = fmaf(p, t, -3.758186102e-01f);
+  p = fmaf(p, t, 1.128362894e+00f);
+  const float e = copysignf(fminf(z * p, 1.0f), x);  // erf(x / sqrt(2))
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
 }
 
 }  // namespace cap4d

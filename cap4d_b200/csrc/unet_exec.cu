@@ -624,7 +624,7 @@ struct Unet {
     const int n_img = c.n_img;
     Op op;
     op.cls = CLS_GN;
-    op.launches = 2;
+    op.launches = 1;
     op.flops = 0;
     op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
     op.run = [=](cudaStream_t s) {
@@ -850,6 +850,8 @@ struct Unet {
     if (!c.dry) {
       c.emb_all = c.ptr<float>(emb);
       c.gn_partial = c.ptr<float>(gnp);
+      // the GroupNorm kernel's per-image barrier counters start at zero (it re-zeroes them itself)
+      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(n_img), 0, gnp.bytes - groupnorm_sync_offset(n_img)));
     }
     const int M0 = n_img * H * W;
     // ---- input stage
@@ -1347,6 +1349,7 @@ int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, 
     set_error("cudaMalloc failed");
     return 3;
   }
+  cudaMemset(partial, 0, groupnorm_partial_bytes(n_img));
   int rc = run_timed(
       [&](cudaStream_t s) {
         return launch_groupnorm(x1, C1, x2, C2, n_img, hw, gamma, beta, eps, apply_silu, reinterpret_cast<bf16*>(out),

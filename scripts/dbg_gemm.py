@@ -1,10 +1,11 @@
 import sys, os, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cap4d_b200 import ops
 dev=torch.device('cuda:0')
-for (M,N,K) in [(65536,320,320),(65536,960,320),(65536,320,2880)]:
+for (M,N,K) in [(65536,2560,320),(16384,5120,640),(65536,320,1280),(65536,960,320)]:
     a=torch.randn(M,K,device=dev).to(torch.bfloat16); w=(torch.randn(N,K,device=dev)/K**.5).to(torch.bfloat16)
-    bias=torch.randn(N,device=dev); r=torch.randn(M,N,device=dev)
-    for name,mode,res in [("f32",0,None),("f32 nostore",16,None),("f32 noepi",32,None),("f32+res",0,r),("f32+res nostore",16,r),("bf16",1,None)]:
-        _,ms=ops.gemm(a,w,bias=bias,residual=res,out_mode=mode,time_iters=10)
-        print(f"M={M} N={N} K={K} {name:16s} {ms*1e3:7.1f} us")
+    bias=torch.randn(N,device=dev)
+    for name,mode in [("geglu",2),("geglu noepi",2|32),("bf16",1),("bf16 noepi",1|32),("f32",0)]:
+        if N==320 and "geglu" in name: continue
+        _,ms=ops.gemm(a,w,bias=bias,out_mode=mode,time_iters=10)
+        print(f"M={M} N={N} K={K} {name:14s} {ms*1e3:7.1f} us  {2.0*M*N*K/ms/1e9:7.1f} TF/s")

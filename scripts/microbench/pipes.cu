@@ -23,6 +23,14 @@ __global__ void k(float* out, int iters, long long* cyc) {
       if (MODE == 4) { asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(s)); }  // FMNMX only
       if (MODE == 6) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(a[i]), "f"(s)); a[i] = __uint_as_float(u | 0x3f000000u); }
       if (MODE == 7) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; if (i & 1) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(e), "f"(a[i-1])); m += __uint_as_float(u); } a[i] = e; }
+      if (MODE == 8) { unsigned u = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+      if (MODE == 9) { unsigned u = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+      if (MODE == 10) { // pair: 2 ffma, pack f16x2, ex2.f16x2, unpack+2 fadd
+        if (i & 1) { float x0 = fmaf(a[i-1], 0.999f, -0.1f), x1 = fmaf(a[i], 0.999f, -0.1f); unsigned u;
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(x1), "f"(x0));
+          asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u));
+          float p0, p1; asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(p0), "=f"(p1) : "r"(u));
+          s += p0; m += p1; a[i-1] = p0; a[i] = p1; } }
       if (MODE == 5) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; a[i] = e; asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(e)); }
     }
   }
@@ -54,6 +62,9 @@ int main() {
     run<3>("FFMA+EX2+FADD", w);
     run<5>("FFMA+EX2+FADD+FMNMX", w);
     run<6>("F2FP.BF16x2", w);
+    run<8>("EX2.bf16x2", w);
+    run<9>("EX2.f16x2", w);
+    run<10>("pair f16x2 pipeline (per elem)", w);
     run<7>("FFMA+EX2+FADD+F2FP/2", w);
   }
   return 0;
