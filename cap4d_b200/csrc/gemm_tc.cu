@@ -302,6 +302,214 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  A cluster of two CTAs computes a 256 x BN tile with ONE UMMA per
+// k-step: CTA r stages rows [128 r, 128 r + 128) of A and rows [r BN/2, (r+1) BN/2) of the weight tile
+// in its own shared memory, the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256), and each
+// CTA's TMEM receives its own 128 rows of the accumulator.  Per CTA and k-block the shared memory then
+// sees 16 KiB + BN*64 B written and read instead of 16 KiB + BN*128 B - the single-CTA kernel is bound
+// by exactly that traffic (see pick_tile) - so the tensor pipe can run at (or near) its peak rate.
+// Barriers: both CTAs' TMA loads signal the LEADER's full[stage]; the leader's commits are multicast to
+// both CTAs' empty[stage] / tmem_full[acc]; both CTAs' epilogue threads arrive on the leader's
+// tmem_empty[acc].
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage_bytes = A_SUB_BYTES;
+  const int b_stage_bytes = (p.BN >> 1) * BK * 2;  // this CTA's half of the weight tile
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * a_stage_bytes;
+  SmemTail* tail = reinterpret_cast<SmemTail*>(sB + p.stages * b_stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int pair_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row pair tiles here
+  const int acc_stride = (p.n_acc == 2) ? (TMEM_COLS / 2) : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&tail->full[s], 1);   // leader producer's arrive.expect_tx (+ the tx bytes of both CTAs)
+      mbar_init(&tail->empty[s], 1);  // leader MMA commit (multicast)
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tail->tmem_full[a], 1);     // leader MMA commit (multicast)
+      mbar_init(&tail->tmem_empty[a], 512);  // epilogue threads of BOTH CTAs (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(&tail->tmem_base, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM allocations exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = 2u * (a_stage_bytes + b_stage_bytes);  // both CTAs' loads land on the leader's barrier
+      const int b_half = p.BN >> 1;
+      for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters) {
+        const int m_tile = pt / p.tiles_n;
+        const int n_tile = pt - m_tile * p.tiles_n;
+        const int row0 = m_tile * 2 * BM + static_cast<int>(rank) * BM;  // first output row of this CTA's half
+        int n0 = 0, y0 = 0;
+        if (p.a_conv) {
+          const int hw = p.H * p.W;
+          n0 = row0 / hw;
+          y0 = (row0 - n0 * hw) / p.W;
+        }
+        const int b_row = n_tile * p.BN + static_cast<int>(rank) * b_half;
+        int tap = 0, c0 = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          if (leader_cta) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+          uint8_t* dstA = sA + stage * a_stage_bytes;
+          if (kb < p.seg0_kb) {
+            if (p.a_conv) {
+              tma_load_4d_2sm(dstA, &tmA, &tail->full[stage], c0, p.tap_dx[tap], y0 + p.tap_dy[tap], n0 + p.tap_dn[tap]);
+              c0 += BK;
+              if (c0 == p.cin_kb * BK) {
+                c0 = 0;
+                ++tap;
+              }
+            } else {
+              tma_load_2d_2sm(dstA, &tmA, &tail->full[stage], kb * BK, row0);
+            }
+          } else {
+            tma_load_2d_2sm(dstA, &tmA2, &tail->full[stage], (kb - p.seg0_kb) * BK, row0);
+          }
+          tma_load_2d_2sm(sB + stage * b_stage_bytes, &tmB, &tail->full[stage], kb * BK, b_row);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader_cta) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN, 0);
+      const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = umma_smem_desc_sw128(smem_u32(sB));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++it) {
+        const int acc = (p.n_acc == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * a_stage_bytes) >> 4);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&tail->empty[stage], 0x3);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tail->tmem_full[acc], 0x3);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs: own 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool geglu = (p.out_mode & 15) == OUT_GEGLU_BF16;
+    const int tcols = geglu ? 64 : 32;
+    const int nchunks = p.BN / tcols;
+    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
+    const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+    int it = 0;
+    for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++it) {
+      const int m_tile = pt / p.tiles_n;
+      const int n_tile = pt - m_tile * p.tiles_n;
+      const int acc = (p.n_acc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(&tail->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
+      const int row = m_tile * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      uint32_t v[32], vg[32];
+      if (c_begin < c_end) {
+        tmem_ld32(taddr + c_begin * tcols, v);
+        if (geglu) tmem_ld32(taddr + c_begin * tcols + 32, vg);
+      }
+      for (int c = c_begin; c < c_end; ++c) {
+        tmem_ld_wait();
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+        if (geglu) {
+          float ag[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ag[j] = __uint_as_float(vg[j]);
+          if (c + 1 < c_end) {
+            tmem_ld32(taddr + (c + 1) * tcols, v);
+            tmem_ld32(taddr + (c + 1) * tcols + 32, vg);
+          }
+          if (row_ok) {
+            const int col0 = n_tile * p.BN + c * 64;
+            if (p.bias != nullptr) {
+              add_vec32(a, p.bias + col0);
+              add_vec32(ag, p.bias + col0 + 32);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = a[j] * gelu_erf_f(ag[j]);
+            epilogue_store_bf16(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col0 >> 1), a);
+          }
+        } else {
+          if (c + 1 < c_end) tmem_ld32(taddr + (c + 1) * tcols, v);
+          if (row_ok) {
+            const int col0 = n_tile * p.BN + c * 32;
+            if (p.residual != nullptr) add_vec32(a, p.residual + static_cast<size_t>(row) * p.ldr + col0);
+            if (p.rowbias != nullptr)
+              add_vec32(a, p.rowbias + static_cast<size_t>(row / p.rowbias_div) * p.rowbias_ld + col0);
+            if (p.bias != nullptr) add_vec32(a, p.bias + col0);
+            if ((p.out_mode & 15) == OUT_F32) {
+              epilogue_store_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
+            } else {
+              epilogue_store_bf16(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&tail->tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair may still touch its smem / barriers / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -365,7 +573,7 @@ int sm_count() {
 namespace {
 
 struct TileCfg {
-  int msub, bn, n_acc;
+  int msub, bn, n_acc, two_cta;
 };
 
 // Pick (msub, BN).  Measured on B200 (scripts/bench_shapes.py, profiles/): the main loop of this
@@ -376,13 +584,17 @@ struct TileCfg {
 TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
   const int sms = sm_count();
-  TileCfg best{0, 0, 0};
-  if (const char* f = getenv("CAP4D_GEMM_FORCE")) {  // "msub,bn" for experiments
-    int ms = 0, bn = 0;
-    if (sscanf(f, "%d,%d", &ms, &bn) == 2 && (ms == 1 || ms == 2) && bn > 0 && N % bn == 0 && bn % 32 == 0 &&
-        bn <= 256 && (!geglu || bn % 64 == 0))
-      return TileCfg{ms, bn, (ms * bn <= 256) ? 2 : 1};
+  TileCfg best{0, 0, 0, 0};
+  if (const char* f = getenv("CAP4D_GEMM_FORCE")) {  // "msub,bn[,two_cta]" for experiments
+    int ms = 0, bn = 0, tc = 0;
+    const int nf = sscanf(f, "%d,%d,%d", &ms, &bn, &tc);
+    if (nf >= 2 && (ms == 1 || ms == 2) && bn > 0 && N % bn == 0 && bn % 32 == 0 && bn <= 256 &&
+        (!geglu || bn % 64 == 0)) {
+      if (nf == 3 && tc == 1 && bn % 64 == 0) return TileCfg{1, bn, 2, 1};
+      return TileCfg{ms, bn, (ms * bn <= 256) ? 2 : 1, 0};
+    }
   }
+  const bool allow_2cta = getenv("CAP4D_GEMM_NO_2CTA") == nullptr;
   double best_cost = 1e30;
   for (int msub = 1; msub <= 2; ++msub) {
     const int tiles_m = (M + msub * BM - 1) / (msub * BM);
@@ -400,7 +612,29 @@ TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
       const double cost = waves * per_tile;
       if (cost < best_cost * 0.999) {
         best_cost = cost;
-        best = TileCfg{msub, bn, n_acc};
+        best = TileCfg{msub, bn, n_acc, 0};
+      }
+    }
+  }
+  // CTA pairs: 256 x BN per cluster, 74 clusters; per CTA and k-block 2*(16 KiB + BN*64 B) of smem traffic.
+  // Measured (scripts/bench_shapes.py with CAP4D_GEMM_FORCE=1,256,1): the pair kernel reaches ~1400 TFLOP/s
+  // at BN = 256, 1.45x the time this model predicts (the tensor pipe tops out near 60 % of its nominal rate
+  // under the power cap), so it only wins where BN = 256 divides N and the pair tiles fill the 74 clusters.
+  if (allow_2cta) {
+    const int slots = std::max(1, sms / 2);
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+    for (int bn : cands) {
+      if (N % bn != 0 || bn % 64 != 0) continue;  // each CTA's half must stay a multiple of the 8-row swizzle group
+      const long tiles = static_cast<long>(tiles_m) * (N / bn);
+      const long waves = (tiles + slots - 1) / slots;
+      const double mma = 2.0 * bn;
+      const double smem = (2.0 * 16384.0 + 2.0 * bn * 64.0) / 128.0;
+      const double epi = 8.0 * bn;
+      const double per_tile = std::max(1.45 * num_kb * std::max(mma, smem) + 800.0, epi);
+      const double cost = waves * per_tile;
+      if (cost < best_cost * 0.99) {
+        best_cost = cost;
+        best = TileCfg{1, bn, 2, 1};
       }
     }
   }
@@ -425,10 +659,12 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
   p.BN = bn;
   p.msub = cfg.msub;
   p.n_acc = cfg.n_acc;
-  p.tiles_m = (p.M + cfg.msub * BM - 1) / (cfg.msub * BM);
+  plan->two_cta = cfg.two_cta;
+  const int rows_per_tile = cfg.two_cta ? 2 * BM : cfg.msub * BM;
+  p.tiles_m = (p.M + rows_per_tile - 1) / rows_per_tile;
   p.tiles_n = N / bn;
   p.num_kb = Ktot / BK;
-  const int stage_bytes = cfg.msub * A_SUB_BYTES + bn * BK * 2;
+  const int stage_bytes = cfg.two_cta ? (A_SUB_BYTES + (bn / 2) * BK * 2) : (cfg.msub * A_SUB_BYTES + bn * BK * 2);
   int stages = (220 * 1024 - static_cast<int>(sizeof(SmemTail)) - 1024) / stage_bytes;
   stages = std::min(stages, MAX_STAGES);
   stages = std::min(stages, std::max(2, p.num_kb));
@@ -443,12 +679,13 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
   p.rowbias_ld = rowbias_ld;
   p.residual = residual;
   p.ldr = ldr;
-  plan->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
+  plan->grid = cfg.two_cta ? 2 * std::min(p.tiles_m * p.tiles_n, std::max(1, sm_count() / 2))
+                           : std::min(p.tiles_m * p.tiles_n, sm_count());
   plan->flops = 2.0 * p.M * static_cast<double>(N) * Ktot;
   // weights: [N][Ktot] row-major
   uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};
   uint64_t strides[2] = {1, static_cast<uint64_t>(Ktot)};
-  uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+  uint32_t box[2] = {BK, static_cast<uint32_t>(cfg.two_cta ? bn / 2 : bn)};
   return make_tmap_bf16(&plan->tmB, Wt, 2, dims, strides, box);
 }
 
@@ -555,9 +792,14 @@ cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
+  if (plan.two_cta)
+    gemm_tc_2sm_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
+  else
+    gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
   return cudaGetLastError();
 }
 

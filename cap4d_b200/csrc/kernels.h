@@ -57,6 +57,7 @@ struct GemmParams {
 struct GemmPlan {
   CUtensorMap tmA, tmA2, tmB;
   GemmParams p;
+  int two_cta;  // 1: CTA-pair kernel (cta_group::2), tiles_m counts 256-row tiles
   int grid;
   size_t smem_bytes;
   double flops;  // 2*M*N*K, for reporting
