@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-gen", type=int, default=840)
-    ap.add_argument("--groups-per-call", type=int, default=2)
+    ap.add_argument("--groups-per-call", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--record-every", type=int, default=4, help="record per-launch events on every n-th U-Net call")
     args = ap.parse_args()
