@@ -61,6 +61,9 @@ SIGNATURES = {
     "cap4d_b200_conv3x3_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                 c_void_p, POINTER(c_float), c_int]),
+    "cap4d_b200_upsample_conv3x3_bf16": (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_float),
+                c_int]),
     "cap4d_b200_attention_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, POINTER(c_float), c_int]),
     "cap4d_b200_attention_trace": (

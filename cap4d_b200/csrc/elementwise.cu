@@ -176,6 +176,37 @@ __global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int co
   }
 }
 
+// ---- folded upsample-conv weights (openaimodel.py:111-119) ---------------------------------------
+// phase py: output row 2y+py reads low-res rows {y-1 (ky=0), y (ky=1,2)} if py == 0, {y (ky=0,1), y+1 (ky=2)} if py == 1
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int O, int I, bf16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(4) * O * 4 * I;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % I);
+    const int tap = static_cast<int>((idx / I) % 4);
+    const size_t o = (idx / (static_cast<size_t>(4) * I)) % O;
+    const int phase = static_cast<int>(idx / (static_cast<size_t>(4) * I * O));
+    const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+    // 3x3 taps merged into low-res tap a (rows) / b (columns)
+    const int ky0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+    const int ky1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+    const int kx1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += w[((o * I + i) * 3 + ky) * 3 + kx];
+    out[idx] = __float2bfloat16(acc);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, size_t n4, bf16* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
 // ---- CFG + DDIM update with scatter: cap4d/mmdm/sampler.py:205-231 -----------------------------
 // eps layout: [2*n_groups][V][chw]; batch b < n_groups = unconditional half of group b,
 // b + n_groups = conditional half.  Only views R..V-1 are generated.
@@ -279,6 +310,21 @@ cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, i
                                     int k_offset, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(O) * I * KH * KW;
   pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(16) * O * I;
+  pack_upconv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t stream) {
+  if (n % 4 != 0) {
+    set_error("cast_bf16: element count must be a multiple of 4");
+    return cudaErrorInvalidValue;
+  }
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(x, n / 4, out);
   return cudaGetLastError();
 }
 

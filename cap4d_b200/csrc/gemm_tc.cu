@@ -81,6 +81,14 @@ __device__ __forceinline__ void add_vec32(float* acc, const float* __restrict__ 
   for (int j = 0; j < 32; ++j) acc[j] += b[j];
 }
 
+// folded upsample: low-res pixel row (n, y, x) -> row of pixel (n, 2y+py, 2x+px) in the 2H x 2W output
+__device__ __forceinline__ int up_row(int row, int H, int W, int py, int px) {
+  const int hw = H * W;
+  const int n = row / hw, rem = row - n * hw;
+  const int y = rem / W, x = rem - y * W;
+  return (n * 2 * H + 2 * y + py) * 2 * W + 2 * x + px;
+}
+
 // A CTA tile is (msub * 128) x BN: msub in {1, 2} 128-row sub-tiles share one B (weight) tile per k-block,
 // which raises the FLOPs per byte streamed from L2 - the resource this kernel is bound by - from
 // 2*128*BN*64 / (16K + 128 BN) to 2*256*BN*64 / (32K + 128 BN).
@@ -247,8 +255,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int cc = c_begin; cc < c_end; ++cc) {
         const int sub = cc / cps, c = cc - sub * cps;
-        const int row = (m_tile * p.msub + sub) * BM + q * 32 + lane;
-        const bool row_ok = row < p.M && !dbg_noepi;
+        const int row_in = (m_tile * p.msub + sub) * BM + q * 32 + lane;
+        const bool row_ok = row_in < p.M && !dbg_noepi;
+        const int row = (p.up_py < 0) ? row_in : up_row(row_in, p.H, p.W, p.up_py, p.up_px);
         tmem_ld_wait();
         float a[32];
 #pragma unroll
@@ -449,8 +458,9 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
-      const int row = m_tile * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_in = m_tile * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
+      const bool row_ok = row_in < p.M;
+      const int row = (p.up_py < 0) ? row_in : up_row(row_in, p.H, p.W, p.up_py, p.up_px);
       uint32_t v[32], vg[32];
       if (c_begin < c_end) {
         tmem_ld32(taddr + c_begin * tcols, v);
@@ -719,7 +729,10 @@ bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2,
     plan->tmA2 = plan->tmA;
     K2 = 0;
   }
-  return finish_plan(plan, Wt, N, K + K2, out_mode, out, ldo, bias, rowbias, rowbias_div, rowbias_ld, residual, ldr);
+  if (!finish_plan(plan, Wt, N, K + K2, out_mode, out, ldo, bias, rowbias, rowbias_div, rowbias_ld, residual, ldr))
+    return false;
+  p.up_py = p.up_px = -1;
+  return true;
 }
 
 bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, const bf16* A2, int K2,
@@ -737,21 +750,33 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
     set_error("conv: Cin must be a multiple of 64");
     return false;
   }
-  if (g.taps != 9 || (g.stride != 1 && g.stride != 2)) {
-    set_error("conv: only 3x3 stride 1/2 is implemented");
+  const bool up = g.up_phase >= 0;
+  if ((!up && g.taps != 9) || (up && (g.taps != 4 || g.stride != 1 || g.up_phase > 3)) ||
+      (g.stride != 1 && g.stride != 2)) {
+    set_error("conv: only 3x3 stride 1/2 and the folded upsample phases are implemented");
     return false;
   }
+  const int ntaps = up ? 4 : 9;
   p.M = g.n_img * H * W;
   p.a_conv = 1;
   p.cin_kb = Cin / BK;
-  p.seg0_kb = 9 * p.cin_kb;
+  p.seg0_kb = ntaps * p.cin_kb;
   p.W = W;
   p.H = H;
   p.box_h = std::min(H, BM / W);
   p.box_n = BM / (W * p.box_h);
-  p.n_taps = 9;
+  p.n_taps = ntaps;
   int planes = 1;
-  for (int ky = 0; ky < 3; ++ky) {
+  if (up) {
+    const int py = g.up_phase >> 1, px = g.up_phase & 1;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        p.tap_dy[a * 2 + b] = a - 1 + py;  // py = 0: rows y-1, y;  py = 1: rows y, y+1
+        p.tap_dx[a * 2 + b] = b - 1 + px;
+        p.tap_dn[a * 2 + b] = 0;
+      }
+  }
+  for (int ky = 0; ky < 3 && !up; ++ky) {
     for (int kx = 0; kx < 3; ++kx) {
       const int t = ky * 3 + kx;
       if (g.stride == 1) {
@@ -783,8 +808,16 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
     plan->tmA2 = plan->tmA;
     K2 = 0;
   }
-  return finish_plan(plan, Wt, N, 9 * Cin + K2, out_mode, out, ldo, bias, rowbias, rowbias_div, rowbias_ld,
-                     residual, ldr);
+  if (!finish_plan(plan, Wt, N, ntaps * Cin + K2, out_mode, out, ldo, bias, rowbias, rowbias_div, rowbias_ld,
+                   residual, ldr))
+    return false;
+  p.up_py = up ? (g.up_phase >> 1) : -1;
+  p.up_px = up ? (g.up_phase & 1) : -1;
+  if (up && (residual != nullptr || rowbias != nullptr)) {
+    set_error("conv: the folded upsample phases support bias only");
+    return false;
+  }
+  return true;
 }
 
 cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {

@@ -43,6 +43,7 @@ struct GemmParams {
   int n_taps;
   int tap_dx[9], tap_dy[9], tap_dn[9];  // coordinate offsets per tap (dn: image-index offset, parity planes)
   int stages;        // smem pipeline depth
+  int up_py, up_px;  // >= 0: output rows are scattered to phase (py, px) of the 2H x 2W grid (folded upsample)
   // epilogue
   int out_mode;
   void* out;          // fp32 or bf16, row-major, leading dimension ldo
@@ -67,6 +68,10 @@ struct ConvGeom {
   int n_img, H, W;    // output grid
   int taps;           // 1 (1x1 / plain) or 9
   int stride;         // 1 or 2 (2: A holds the 4 parity planes [4][n_img][H][W][C])
+  // up_phase >= 0: one phase (py = up_phase / 2, px = up_phase % 2) of "nearest-2x upsample then conv3x3"
+  // folded into a 2x2-tap conv on the LOW-resolution grid H x W; taps = 4, weights [Cout][4*Cin] are the
+  // phase-summed 3x3 taps, and output row (n, y, x) is written to pixel (n, 2y+py, 2x+px) of the 2H x 2W map
+  int up_phase = -1;
 };
 
 // Plain GEMM: A [M][K] bf16 (lda == K), optional second segment A2 [M][K2].
@@ -153,6 +158,11 @@ cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long 
 // fp32 -> bf16 weight repacks (device side)
 cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
                                     int k_offset, cudaStream_t stream);  // out[o][k_offset + (kh*KW+kw)*I + i]
+// nearest-2x-upsample + conv3x3 folded: out[phase][o][(a*2+b)*I + i] = sum of the 3x3 taps that fall on
+// low-res tap (a, b) of phase (py, px); out is [4][O][4*I] bf16
+cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream);
+// fp32 -> bf16 copy
+cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t stream);
 cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, int ldk, int k_offset, int row_offset,
                                cudaStream_t stream);                     // out[row_offset + r][k_offset + c]
 

@@ -533,11 +533,15 @@ struct Unet {
     for (int pass = 0; pass < 2; ++pass) {
       for (ConvW& c : (pass == 0 ? down : up)) {
         if (!get(c.prefix + "weight", static_cast<size_t>(c.cout) * c.cin * 9, &t)) return false;
-        c.w = dev_alloc<bf16>(static_cast<size_t>(c.cout) * 9 * c.cin);
+        // up: nearest-2x + conv3x3 is folded into four 2x2-tap phase convs on the low-res grid: [4][Cout][4*Cin]
+        c.w = dev_alloc<bf16>(static_cast<size_t>(c.cout) * (pass == 0 ? 9 : 16) * c.cin);
         if (!c.w) {
           set_error("cudaMalloc failed");
           return false;
         }
+        if (pass == 1) {
+          CUDA_OK(launch_pack_upconv_weight(t->d, c.cout, c.cin, c.w, 0));
+        } else
         CUDA_OK(launch_pack_conv_weight(t->d, c.cout, c.cin, 3, 3, c.w, 9 * c.cin, 0, 0));
         consumed.push_back(c.prefix + "weight");
         if (!fp(c.prefix + "bias", c.cout, &c.b)) return false;
@@ -769,30 +773,36 @@ struct Unet {
     return true;
   }
 
-  // Upsample (openaimodel.py:92-120): nearest 2x, conv3x3
+  // Upsample (openaimodel.py:92-120): nearest 2x, conv3x3.  Folded: output pixel (2y+py, 2x+px) only sees a
+  // 2x2 neighbourhood of the low-res input, so each of the four phases is a 4-tap conv with pre-summed
+  // weights (4/9 of the FLOPs, and the 4x upsampled tensor is never written).
   bool plan_up(PlanCtx& c, const ConvW& w, const Buf& x, int H, int W, Buf* out) {
     const int C = w.cin;
-    Buf upb = c.alloc(x.M * 4, C, 2);
+    Buf xb = c.alloc(x.M, C, 2);
     *out = c.alloc(x.M * 4, w.cout, 4);
     if (!c.dry) {
       const float* px = c.ptr<float>(x);
-      bf16* pu = c.ptr<bf16>(upb);
-      const int n_img = c.n_img;
+      bf16* pb = c.ptr<bf16>(xb);
+      const size_t n = static_cast<size_t>(x.M) * C;
       Op op;
       op.cls = CLS_OTHER;
       op.launches = 1;
       op.flops = 0;
-      op.bytes = static_cast<double>(x.M) * C * (4 + 8);
-      op.run = [=](cudaStream_t s) { return launch_upsample2x_bf16(px, n_img, H, W, C, pu, s); };
+      op.bytes = static_cast<double>(n) * 6;
+      op.run = [=](cudaStream_t s) { return launch_cast_bf16(px, n, pb, s); };
       c.ops->push_back(op);
-      GemmPlan p;
-      ConvGeom g{c.n_img, 2 * H, 2 * W, 9, 1};
-      if (!make_conv_plan(&p, pu, g, C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1,
-                          0, nullptr, 0))
-        return false;
-      add_gemm_op(c, CLS_CONV, p);
+      for (int phase = 0; phase < 4; ++phase) {
+        GemmPlan p;
+        ConvGeom g{c.n_img, H, W, 4, 1};
+        g.up_phase = phase;
+        if (!make_conv_plan(&p, pb, g, C, nullptr, 0, w.w + static_cast<size_t>(phase) * w.cout * 4 * C, w.cout, OUT_F32,
+                            c.ptr<float>(*out), w.cout, w.b, nullptr, 1, 0, nullptr, 0))
+          return false;
+        p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C;  // algorithmic: the un-folded conv's share
+        add_gemm_op(c, CLS_CONV, p);
+      }
     }
-    c.release(upb);
+    c.release(xb);
     return true;
   }
 
@@ -1320,6 +1330,44 @@ int cap4d_b200_conv3x3_bf16(const uint16_t* A, const uint16_t* Wt, int n_img, in
                       OUT_F32, out, Cout, bias, rowbias, H_out * W_out, Cout, residual, Cout))
     return 10;
   return run_timed([&](cudaStream_t s) { return launch_gemm(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+int cap4d_b200_upsample_conv3x3_bf16(const uint16_t* A, const float* w_oihw, int n_img, int H, int W, int Cin, int Cout,
+                                     const float* bias, float* out, void* stream, float* ms_out, int iters) {
+  bf16* wp = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&wp), static_cast<size_t>(16) * Cout * Cin * sizeof(bf16)) != cudaSuccess) {
+    set_error("cudaMalloc failed");
+    return 3;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_pack_upconv_weight(w_oihw, Cout, Cin, wp, s);
+  GemmPlan plans[4];
+  int rc = 0;
+  for (int phase = 0; phase < 4 && rc == 0; ++phase) {
+    ConvGeom g{n_img, H, W, 4, 1};
+    g.up_phase = phase;
+    if (!make_conv_plan(&plans[phase], reinterpret_cast<const bf16*>(A), g, Cin, nullptr, 0,
+                        wp + static_cast<size_t>(phase) * Cout * 4 * Cin, Cout, OUT_F32, out, Cout, bias, nullptr, 1, 0,
+                        nullptr, 0))
+      rc = 10;
+  }
+  if (rc == 0 && e == cudaSuccess) {
+    rc = run_timed(
+        [&](cudaStream_t st) {
+          for (int phase = 0; phase < 4; ++phase) {
+            cudaError_t le = launch_gemm(plans[phase], st);
+            if (le != cudaSuccess) return le;
+          }
+          return cudaSuccess;
+        },
+        s, ms_out, iters);
+  } else if (rc == 0) {
+    set_error(cudaGetErrorString(e));
+    rc = 8;
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(wp);
+  return rc;
 }
 
 int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,

@@ -66,6 +66,25 @@ def conv3x3(a_nhwc: torch.Tensor, w_packed: torch.Tensor, n_img: int, H_out: int
     return (out, ms.value) if time_iters else out
 
 
+def upsample_conv3x3(a_nhwc: torch.Tensor, w_oihw: torch.Tensor, bias=None, time_iters: int = 0):
+    """nearest-2x upsample + 3x3 conv (pad 1), folded into four 2x2-tap phase convs.
+    a_nhwc: bf16 [n,H,W,Cin] (low resolution); w_oihw: fp32 [Cout,Cin,3,3].  Returns fp32 [n*2H*2W, Cout]."""
+    _check_cuda(a_nhwc, w_oihw, bias)
+    n, H, W, Cin = a_nhwc.shape
+    Cout = w_oihw.shape[0]
+    w32 = w_oihw.to(torch.float32).contiguous()
+    out = torch.empty((n * 4 * H * W, Cout), device=a_nhwc.device, dtype=torch.float32)
+    ms = ctypes.c_float(0)
+    lib = _lib.load()
+    _lib.check(
+        lib.cap4d_b200_upsample_conv3x3_bf16(_ptr(a_nhwc), _ptr(w32), n, H, W, Cin, Cout, _ptr(bias), _ptr(out),
+                                             _stream(out.device), ctypes.byref(ms) if time_iters else None,
+                                             max(1, time_iters)),
+        "upsample_conv3x3_bf16",
+    )
+    return (out, ms.value) if time_iters else out
+
+
 def pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     """[O,I,3,3] fp32 -> bf16 [O, 9*I] with K index = (ky*3+kx)*I + i (what the conv kernel expects)."""
     O, I, KH, KW = w_oihw.shape

@@ -113,6 +113,12 @@ int cap4d_b200_conv3x3_bf16(const uint16_t* A, const uint16_t* Wt, int n_img, in
                             int stride, const float* bias, const float* rowbias, const float* residual, float* out,
                             void* stream, float* ms_out, int iters);
 
+/* Upsample (openaimodel.py:92-120): F.interpolate(scale 2, nearest) then Conv2d(3, pad 1), evaluated as four
+ * 2x2-tap phase convolutions on the low-resolution NHWC bf16 input [n_img][H][W][Cin]; w_oihw is the fp32
+ * [Cout][Cin][3][3] device tensor (phase-summed and packed internally); out fp32 [n_img*2H*2W][Cout]. */
+int cap4d_b200_upsample_conv3x3_bf16(const uint16_t* A, const float* w_oihw, int n_img, int H, int W, int Cin, int Cout,
+                                     const float* bias, float* out, void* stream, float* ms_out, int iters);
+
 /* legacy_attention (attention.py:112-132) for head_dim 64 on the fused qkv matrix [M][3C];
  * sequences are L consecutive rows. */
 int cap4d_b200_attention_bf16(const uint16_t* qkv, uint16_t* out, int M, int C, int L, float scale, void* stream,

@@ -125,6 +125,22 @@ def test_conv3x3_stride2(ops, cuda_device, n_img, H, W, C):
     assert _rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n_img,H,W,C", [(2, 32, 32, 64), (4, 8, 8, 128), (8, 2, 2, 64), (16, 16, 16, 1280)])
+def test_upsample_conv3x3(ops, cuda_device, n_img, H, W, C):
+    # Upsample (openaimodel.py:111-119): nearest 2x then conv3x3; here four phase convs with pre-summed taps.
+    # The summed taps are rounded to bf16 once, so the comparison uses the same summed-then-rounded weights.
+    g = torch.Generator().manual_seed(H + C)
+    x = torch.randn(n_img, C, H, W, generator=g).to(cuda_device).to(torch.bfloat16)
+    w = (torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(cuda_device)
+    bias = torch.randn(C, generator=g).to(cuda_device)
+    out = ops.upsample_conv3x3(x.permute(0, 2, 3, 1).contiguous(), w, bias=bias)
+    up = F.interpolate(x.double(), scale_factor=2, mode="nearest")
+    exact = F.conv2d(up, w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    # exact-weight reference: only the bf16 rounding of the (summed) weights separates the two
+    assert _rel(out, exact) < 6e-3
+    assert float((out.double() - exact).norm() / exact.norm()) < 3e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------
