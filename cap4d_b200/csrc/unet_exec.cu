@@ -184,8 +184,16 @@ struct Unet {
   int pB = 0, pV = 0, pH = 0, pW = 0;
   void* p_ws = nullptr;
   size_t p_ws_bytes = 0;
+  struct CachedPlan {
+    int B, V, H, W;
+    void* ws;
+    size_t ws_bytes;
+    std::vector<Op> ops;
+  };
+  std::vector<CachedPlan> cache;
   std::vector<cudaEvent_t> events;
   std::vector<std::vector<cudaEvent_t>> deferred, event_pool;
+  std::vector<std::vector<int>> deferred_cls;  // op classes of the plan each deferred run used
 
   ~Unet() {
     for (void* p : owned) cudaFree(p);
@@ -982,6 +990,24 @@ struct Unet {
       return false;
     }
     if (B == pB && V == pV && H == pH && W == pW && ws == p_ws && ws_bytes == p_ws_bytes && !ops.empty()) return true;
+    // park the current plan and look for a cached one (a sampler alternates between at most a few batch
+    // shapes, e.g. 4 groups per call and a 3-group remainder; each shape has its own workspace)
+    if (!ops.empty()) {
+      if (cache.size() >= 4) cache.erase(cache.begin());
+      cache.emplace_back();
+      CachedPlan& cp = cache.back();
+      cp.B = pB, cp.V = pV, cp.H = pH, cp.W = pW, cp.ws = p_ws, cp.ws_bytes = p_ws_bytes;
+      cp.ops.swap(ops);
+    }
+    for (size_t i = 0; i < cache.size(); ++i) {
+      CachedPlan& cp = cache[i];
+      if (cp.B == B && cp.V == V && cp.H == H && cp.W == W && cp.ws == ws && cp.ws_bytes == ws_bytes) {
+        ops.swap(cp.ops);
+        pB = B, pV = V, pH = H, pW = W, p_ws = ws, p_ws_bytes = ws_bytes;
+        cache.erase(cache.begin() + i);
+        return true;
+      }
+    }
     size_t need = 0;
     if (!workspace_bytes(B, V, H, W, &need)) return false;
     if (ws == nullptr || ws_bytes < need) {
@@ -1023,6 +1049,8 @@ struct Unet {
         deferred.emplace_back();
       }
       evs = &deferred.back();
+      deferred_cls.emplace_back();
+      for (const Op& op : ops) deferred_cls.back().push_back(op.cls);
     }
     if (evs != nullptr) {
       while (evs->size() < ops.size() + 1) {
@@ -1060,14 +1088,21 @@ struct Unet {
   bool collect_timings(float* class_ms, int* n_runs) {
     for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) class_ms[k] = 0.f;
     *n_runs = 0;
-    for (auto& evs : deferred) {
-      if (evs.size() < ops.size() + 1) continue;
-      CUDA_OK(cudaEventSynchronize(evs[ops.size()]));
-      if (!accumulate(evs, class_ms)) return false;
+    for (size_t r = 0; r < deferred.size(); ++r) {
+      const std::vector<cudaEvent_t>& evs = deferred[r];
+      const std::vector<int>& cls = deferred_cls[r];
+      if (evs.size() < cls.size() + 1) continue;
+      CUDA_OK(cudaEventSynchronize(evs[cls.size()]));
+      for (size_t i = 0; i < cls.size(); ++i) {
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+        class_ms[cls[i]] += ms;
+      }
       ++*n_runs;
     }
     for (auto& evs : deferred) event_pool.push_back(std::move(evs));
     deferred.clear();
+    deferred_cls.clear();
     return true;
   }
 };

@@ -70,8 +70,7 @@ class B200MMDMUnet(torch.nn.Module):
         self._device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self._lib = _lib.load()
         self._handle = ctypes.c_void_p()
-        self._ws: Optional[torch.Tensor] = None
-        self._ws_key = None
+        self._ws: Dict = {}  # (B, V, H, W) -> workspace tensor (a launch plan is bound to its workspace)
         self.dtype = torch.float32
         self.time_steps = int(config["time_steps"])
         cfg = _make_config(config)
@@ -158,14 +157,16 @@ class B200MMDMUnet(torch.nn.Module):
 
     def _workspace(self, B, V, H, W) -> torch.Tensor:
         key = (B, V, H, W)
-        if self._ws is None or self._ws_key != key:
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:  # the library caches 4 plans as well
+                self._ws.pop(next(iter(self._ws)))
             n = ctypes.c_size_t()
             _lib.check(self._lib.cap4d_b200_unet_workspace_bytes(self._handle, B, V, H, W, ctypes.byref(n)),
                        "workspace_bytes")
-            self._ws = None
-            self._ws = torch.empty(n.value + 2048, dtype=torch.uint8, device=self._device)
-            self._ws_key = key
-        return self._ws
+            ws = torch.empty(n.value + 2048, dtype=torch.uint8, device=self._device)
+            self._ws[key] = ws
+        return ws
 
     def _prep(self, x, timesteps, control):
         if x.dim() != 5:

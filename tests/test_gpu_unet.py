@@ -149,3 +149,21 @@ def test_reference_call_convention(cuda_device, tiny_unets):
     assert eu.shape == (1, 4, 4, 8, 8)
     with pytest.raises(AssertionError):
         unet(x.to(cuda_device), timesteps=t.to(cuda_device), context=torch.zeros(1), control=_to(ctrl, cuda_device))
+
+
+def test_plan_cache_alternating_batch_shapes(cuda_device, tiny_unets):
+    """A sampler whose group count is not a multiple of groups_per_call alternates between two batch
+    shapes; each shape keeps its own launch plan and workspace, and results do not depend on the order."""
+    unet, sd = tiny_unets(0)
+    outs = {}
+    shapes = [(4, 4, 8, 8), (2, 4, 8, 8), (4, 4, 8, 8), (6, 4, 16, 16), (2, 4, 8, 8), (4, 4, 8, 8)]
+    for i, (B, V, H, W) in enumerate(shapes):
+        x, t, ctrl = O.make_inputs(O.TINY_CONFIG, B=B, V=V, H=H, W=W, R=1, seed=B * 100 + H)
+        y = unet(x.to(cuda_device), timesteps=t.to(cuda_device), context=None, control=_to(ctrl, cuda_device))
+        key = (B, V, H, W)
+        if key in outs:
+            assert torch.equal(y, outs[key])
+        else:
+            ref = O.unet_forward(sd, O.TINY_CONFIG, x, t, ctrl)
+            assert O.max_rel_err(y.cpu()[:, 1:], ref[:, 1:]) < EPS_TOL
+            outs[key] = y
