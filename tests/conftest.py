@@ -19,3 +19,13 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The CUDA extension is built in-tree (git-ignored); build it once if this checkout has none.
+    nvcc cross-compiles for sm_100a without a GPU."""
+    from cap4d_b200 import _lib, build
+
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build(verbose=False)

@@ -60,7 +60,10 @@ def test_unet_matches_reference_fixture(cuda_device, tiny_unets, name):
     assert err < EPS_TOL
 
 
-@pytest.mark.parametrize("B,V,H,W,R,tstep", [(2, 4, 32, 32, 1, 11), (4, 4, 16, 16, 2, 771), (1, 4, 8, 8, 3, 1)])
+@pytest.mark.parametrize("B,V,H,W,R,tstep", [(2, 4, 32, 32, 1, 11), (4, 4, 16, 16, 2, 771), (1, 4, 8, 8, 3, 1),
+                                             (2, 4, 16, 32, 1, 501),   # non-square latent
+                                             (2, 2, 16, 16, 1, 41),    # fewer views than the model's time_steps
+                                             (1, 6, 8, 8, 2, 999)])    # more views, odd batch
 def test_unet_matches_oracle(cuda_device, tiny_unets, B, V, H, W, R, tstep):
     unet, sd = tiny_unets(0)
     x, t, ctrl = O.make_inputs(O.TINY_CONFIG, B=B, V=V, H=H, W=W, R=R, seed=B * 10 + H, timestep=tstep)

@@ -100,6 +100,20 @@ def test_schedule_bit_exact():
         ddim_factors(s.alphas_cumprod, 3)
 
 
+def test_ddim_factors_with_eta_match_oracle():
+    # eta only changes the e_t coefficient (there is no sigma * noise term in sampler.py:215-231)
+    from cap4d_b200 import MMDMSchedule, ddim_factors
+
+    s = MMDMSchedule()
+    for S, eta in ((10, 0.5), (20, 1.0)):
+        steps, xf, ef = ddim_factors(s.alphas_cumprod, S, eta)
+        ts, a, ap, sg = O.ddim_schedule(s.alphas_cumprod.numpy(), S, eta=eta)
+        assert np.array_equal(steps, np.flip(ts))
+        for i in range(S):
+            x_ref, e_ref = O.ddim_coefficients(a, ap, sg, S - 1 - i)
+            assert float(x_ref) == float(xf[i]) and float(e_ref) == float(ef[i])
+
+
 # ---------------------------------------------------------------------------------------------
 # sampler host logic with a torch stand-in for the device kernels
 # ---------------------------------------------------------------------------------------------
