@@ -115,7 +115,7 @@ cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* tr
 // concatenation of two tensors (C1 from x1, C2 from x2); writes bf16
 // [M][C1+C2] = (silu?)(gn(x)) and optionally a raw bf16 copy of x.
 // partial: scratch of groupnorm_partial_bytes(n_img): fp32 [n_img][GN_MAX_CHUNKS][32][2] + barrier counters.
-enum { GN_MAX_CHUNKS = 64 };
+enum { GN_MAX_CHUNKS = 128 };
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
                              cudaStream_t stream);

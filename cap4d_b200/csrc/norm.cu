@@ -5,10 +5,15 @@
 // (openaimodel.py:180-184, 222-231, 770-774; eps 1e-5) and as `Normalize` in the transformer
 // (cap4d/mmdm/net/attention.py:107-109; eps 1e-6, no SiLU); LayerNorm32 at attention.py:311-326.
 //
-// These kernels are HBM-bound: fp32 in (read twice, the second time mostly from L2), bf16 out.
+// These kernels are HBM-bound: fp32 in (GroupNorm: read twice, the second time mostly from L2), bf16 out.
+// (Measured alternative, rejected: keeping each block's slice in shared memory between the two passes
+// via 1-D bulk copies reads HBM once but, with only 2-4 slices per SM, overlaps loads and stores worse -
+// 2.2-2.8 TB/s against 3.4-3.7 TB/s for this version on the production tensors.)
 // The up-path ResBlocks normalise the channel concatenation of two tensors whose 32 groups
 // straddle the seam (openaimodel.py:766 via mmdm_unet.py:115); both sources are read in place and
 // the concatenation only ever exists as the bf16 output.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -24,7 +29,17 @@ struct GnGeom {
   int rows_per_chunk, n_chunks;
 };
 
-__host__ GnGeom gn_geometry(int C1, int C2, int hw) {
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
+// Chunks per image.  Every block pays the fixed latency of the image barrier, so chunks should be as
+// large as keeping the GPU full allows (one wave of resident blocks over all images); large images get
+// more chunks so that the images in flight (resident blocks / chunks per image) stay L2-sized.  The
+// defaults are the best of a measured sweep (scripts/gn_sweep.sh) at 16 and 80 images.
+__host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img) {
+  static const int l2_mb = env_int("CAP4D_GN_L2_MB", 160), waves = env_int("CAP4D_GN_WAVES", 1);
   GnGeom g;
   g.C = C1 + C2;
   g.C1 = C1;
@@ -47,7 +62,13 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw) {
   g.TY = 256 / g.TX;
   if (g.TY < 1) g.TY = 1;
   if (g.TY > hw) g.TY = hw;
-  int rpc = (hw + GN_MAX_CHUNKS - 1) / GN_MAX_CHUNKS;
+  const int resident = 148 * (g.nqi == 1 ? 4 : 3);  // blocks the GPU holds at once (register-limited)
+  const double image_mb = static_cast<double>(hw) * g.C * 4 / (1024.0 * 1024.0);
+  int chunks = static_cast<int>(resident * image_mb / l2_mb) + 1;            // (1) L2 residency
+  const int fill = (waves * resident + n_img - 1) / n_img;                   // (2) enough blocks
+  if (chunks < fill) chunks = fill;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  int rpc = (hw + chunks - 1) / chunks;
   if (rpc < 4 * g.TY) rpc = 4 * g.TY;
   if (rpc > hw) rpc = hw;
   g.rows_per_chunk = rpc;
@@ -324,8 +345,9 @@ cudaError_t launch_gn_t(const GnGeom& g, const float* x1, int C1, const float* x
 
 // per-chunk partials followed by the per-image barrier counters (which must start zeroed, see
 // groupnorm_sync_offset; the kernel leaves them zeroed again)
-size_t groupnorm_partial_bytes(int n_img) {
-  return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float) + static_cast<size_t>(n_img) * 8;
+size_t groupnorm_partial_bytes(int n_img) {  // partials | GnSync[n_img]
+  return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float) +
+         static_cast<size_t>(n_img) * sizeof(GnSync);
 }
 size_t groupnorm_sync_offset(int n_img) { return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float); }
 
@@ -337,7 +359,7 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
     set_error("groupnorm: channels must be a multiple of 32 (each source a multiple of 4)");
     return cudaErrorInvalidValue;
   }
-  GnGeom g = gn_geometry(C1, C2, hw);
+  GnGeom g = gn_geometry(C1, C2, hw, n_img);
   if (g.nqi > GN_MAX_QI || static_cast<size_t>(2) * C * g.TY * sizeof(float) > 48 * 1024) {
     set_error("groupnorm: too many channels for this kernel");
     return cudaErrorInvalidValue;
