@@ -13,7 +13,8 @@
 //   * an optional second plain A segment appends K (the ResBlock's 1x1 skip conv is accumulated
 //     into the same TMEM tile as its second 3x3 conv).
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-9 epilogue.
+// CTA = 384 threads = 3 warpgroups: WG0 = warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-3
+// idle; WG1-2 = warps 4-11 epilogue.  setmaxnreg moves WG0's registers to the epilogue warpgroups (56 / 216).
 // CTA tile (msub*128) x BN; smem ring of `stages` {A msub x 128x64, B BNx64} bf16 tiles (128B swizzle);
 // two TMEM accumulator stages when they fit (msub*BN <= 256) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -33,7 +34,9 @@ constexpr int BM = 128;                     // rows of one UMMA (TMEM lanes)
 constexpr int BK = 64;
 constexpr int A_SUB_BYTES = BM * BK * 2;    // 16 KiB: one 128-row A sub-tile
 constexpr int MAX_STAGES = 8;
-constexpr int GEMM_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GEMM_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4..11 epilogue
+constexpr int EPI_WARP0 = 4;                // first epilogue warp
+constexpr int REGS_CTRL = 56, REGS_EPI = 216;  // 128*56 + 256*216 = 62464 <= 65536
 constexpr int TMEM_COLS = 512;
 
 struct SmemTail {
@@ -43,6 +46,15 @@ struct SmemTail {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // 256-bit global accesses (sm_100): a thread owns a whole accumulator row, so its 32 columns are 4
 // (fp32) or 2 (bf16) 32-byte pieces of ONE 128 B line; wider pieces halve the number of L1 wavefronts the
@@ -132,6 +144,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
+  if (warp < EPI_WARP0) {  // ---- WG0: control warps (the two role blocks below belong to this branch)
+  setmaxnreg_dec<REGS_CTRL>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -223,14 +237,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&tail->tmem_full[acc]);
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
+  }
+  } else {  // ---- WG1-2: epilogue warps
+    setmaxnreg_inc<REGS_EPI>();
+    // ===================== epilogue (warps 4..11) =====================
     // Thread <-> accumulator row (TMEM lane); two warps share each TMEM lane quarter and split the
     // tile's column chunks, so every SM sub-partition has two epilogue warps to hide the
     // tcgen05.ld / global-load latencies.  Each thread reads / writes whole 128 B (fp32) or 64 B (bf16)
     // row segments; the next chunk's tcgen05.ld is in flight while the current one is written out.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the chunks this warp handles
+    const int half = (warp - EPI_WARP0) >> 2;  // which half of the chunks this warp handles
     const bool geglu = (p.out_mode & 15) == OUT_GEGLU_BF16;
     const bool dbg_noepi = (p.out_mode & 32) != 0;
     const int tcols = geglu ? 64 : 32;         // TMEM columns per chunk
@@ -364,6 +380,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
+  if (warp < EPI_WARP0) {  // ---- WG0: control warps (the two role blocks below belong to this branch)
+  setmaxnreg_dec<REGS_CTRL>();
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
@@ -440,10 +458,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         umma_commit_2sm(&tail->tmem_full[acc], 0x3);
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9, both CTAs: own 128 rows) =====================
+  }
+  } else {  // ---- WG1-2: epilogue warps
+    setmaxnreg_inc<REGS_EPI>();
+    // ===================== epilogue (warps 4..11, both CTAs: own 128 rows) =====================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - EPI_WARP0) >> 2;
     const bool geglu = (p.out_mode & 15) == OUT_GEGLU_BF16;
     const int tcols = geglu ? 64 : 32;
     const int nchunks = p.BN / tcols;
@@ -455,12 +475,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int n_tile = pt - m_tile * p.tiles_n;
       const int acc = (p.n_acc == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
-      mbar_wait(&tail->tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
       const int row_in = m_tile * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
       const bool row_ok = row_in < p.M;
       const int row = (p.up_py < 0) ? row_in : up_row(row_in, p.H, p.W, p.up_py, p.up_px);
+      mbar_wait(&tail->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
       uint32_t v[32], vg[32];
       if (c_begin < c_end) {
         tmem_ld32(taddr + c_begin * tcols, v);

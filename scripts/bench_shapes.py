@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cap4d_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-N_IMG = 16
+N_IMG = int(os.environ.get("N_IMG", "16"))
 
 
 def conv(hw, cin, cout, count, iters=10):

@@ -11,6 +11,7 @@ __global__ void k(float* out, int iters, long long* cyc) {
   float a[16];
   for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
   float s = 0.f, m = -1e30f;
+  unsigned long long acc2 = 0ull;
   __syncthreads();
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -31,11 +32,22 @@ __global__ void k(float* out, int iters, long long* cyc) {
           asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u));
           float p0, p1; asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(p0), "=f"(p1) : "r"(u));
           s += p0; m += p1; a[i-1] = p0; a[i] = p1; } }
+      if (MODE == 11) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; if (i & 1) { unsigned u0 = __float_as_uint(a[i-1]) + 0x8000u, u1 = __float_as_uint(e) + 0x8000u; unsigned u = __byte_perm(u0, u1, 0x7632); m += __uint_as_float(u); } a[i] = e; }
+      if (MODE == 12) { if (i & 1) { // f32x2 FFMA + 2 EX2 + f32x2 FADD + integer pack
+          unsigned long long xx, cc = 0x3f7fbe773f7fbe77ull, dd = 0xbdcccccdbdcccccdull, ss;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(a[i-1]), "f"(a[i]));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(xx) : "l"(cc), "l"(dd));
+          float x0, x1; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+          float e0 = ex2(x0), e1 = ex2(x1);
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(ss) : "f"(e0), "f"(e1));
+          asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2) : "l"(ss));
+          unsigned u = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632); m += __uint_as_float(u);
+          a[i-1] = e0; a[i] = e1; } }
       if (MODE == 5) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; a[i] = e; asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(e)); }
     }
   }
   long long t1 = clock64();
-  float r = s + m;
+  float r = s + m + __uint_as_float((unsigned)acc2) + __uint_as_float((unsigned)(acc2 >> 32));
   for (int i = 0; i < 16; ++i) r += a[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
@@ -66,6 +78,8 @@ int main() {
     run<9>("EX2.f16x2", w);
     run<10>("pair f16x2 pipeline (per elem)", w);
     run<7>("FFMA+EX2+FADD+F2FP/2", w);
+    run<11>("FFMA+EX2+FADD+intpack", w);
+    run<12>("FFMA2+EX2+FADD2+intpack", w);
   }
   return 0;
 }
