@@ -384,4 +384,49 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return fmaf(hx, e, hx);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 process two values per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// y = a * gelu_erf(g) for two (a, g) pairs at once: the same polynomial as gelu_erf_f with the FMA chain
+// issued as FFMA2 (the GEGLU epilogue is bound by issue slots, not by the FMA pipe).
+__device__ __forceinline__ void geglu_pair(float& a0, float& a1, float g0, float g1) {
+  const float z0 = fminf(fabsf(g0) * 0.70710678118654752f, 3.0f);
+  const float z1 = fminf(fabsf(g1) * 0.70710678118654752f, 3.0f);
+  const f32x2 z = pack2(z0, z1);
+  const f32x2 t = mul2(z, z);
+  f32x2 q = fma2(pack2(4.918275920e-08f, 4.918275920e-08f), t, pack2(-2.267730679e-06f, -2.267730679e-06f));
+  q = fma2(q, t, pack2(4.614729187e-05f, 4.614729187e-05f));
+  q = fma2(q, t, pack2(-5.535572418e-04f, -5.535572418e-04f));
+  q = fma2(q, t, pack2(4.437862430e-03f, 4.437862430e-03f));
+  q = fma2(q, t, pack2(-2.564961277e-02f, -2.564961277e-02f));
+  q = fma2(q, t, pack2(1.118625030e-01f, 1.118625030e-01f));
+  q = fma2(q, t, pack2(-3.758186102e-01f, -3.758186102e-01f));
+  q = fma2(q, t, pack2(1.128362894e+00f, 1.128362894e+00f));
+  float e0, e1;
+  unpack2(mul2(z, q), e0, e1);
+  e0 = copysignf(fminf(e0, 1.0f), g0);  // erf(g / sqrt(2))
+  e1 = copysignf(fminf(e1, 1.0f), g1);
+  // a * (0.5 g (1 + erf)) = (0.5 a g) * erf + (0.5 a g)
+  const f32x2 hag = mul2(pack2(a0, a1), pack2(0.5f * g0, 0.5f * g1));
+  unpack2(fma2(hag, pack2(e0, e1), hag), a0, a1);
+}
+
 }  // namespace cap4d

@@ -81,6 +81,29 @@ def test_gemm_geglu(ops, cuda_device):
     assert _rel(out.float(), ref) < 4e-3
 
 
+def test_gemm_tile_configurations_agree(ops, cuda_device, monkeypatch):
+    """Every tile configuration (128- / 256-row CTA tiles, CTA pairs, several BN) and the opt-in
+    autotuner compute the same GEMM: identical k order per output element, so bit-identical results."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 2176, 960, 320  # 17 row tiles (odd: the pair kernel's last tile is half empty)
+    a = torch.randn(M, K, generator=g).to(cuda_device).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    base = ops.gemm(a, w, bias=bias, residual=res)
+    assert _rel(base, ref) < 2e-5
+    for force in ("1,192", "2,96", "1,64", "2,64", "1,192,1", "1,64,1", "2,160"):
+        monkeypatch.setenv("CAP4D_GEMM_FORCE", force)
+        out = ops.gemm(a, w, bias=bias, residual=res)
+        assert torch.equal(out, base), force
+    monkeypatch.delenv("CAP4D_GEMM_FORCE")
+    monkeypatch.setenv("CAP4D_GEMM_AUTOTUNE", "1")
+    tuned = ops.gemm(a, w, bias=bias, residual=res)   # times the candidates, caches the winner
+    tuned2 = ops.gemm(a, w, bias=bias, residual=res)  # cache hit
+    assert torch.equal(tuned, base) and torch.equal(tuned2, base)
+
+
 # ---------------------------------------------------------------------------------------------
 # implicit-GEMM 3x3 convolution
 # ---------------------------------------------------------------------------------------------
