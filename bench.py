@@ -318,7 +318,11 @@ def main():
                 "step": "one DDIM step over all n_gen views; value = n_gen / (S * s_per_step)",
             },
             "unet_step_ms": unet_ms,
-            "unet_tflops": UNET_FLOPS_GROUP * gpc / (unet_ms * 1e-3) / 1e12 if unet_ms else None,
+            # executed FLOPs of the plan (the sampler's calls drop the reference view after the last cross-view
+            # layer: ~3 % fewer FLOPs than the reference's 14.034 TFLOP per group, same outputs)
+            "unet_tflops": sum(v["flops"] for v in stats.values()) / (unet_ms * 1e-3) / 1e12 if unet_ms else None,
+            "unet_flops_per_group": {"executed": sum(v["flops"] for v in stats.values()) / gpc,
+                                     "reference_algorithmic": UNET_FLOPS_GROUP},
             "roofline": {
                 "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

@@ -38,6 +38,7 @@ SIGNATURES = {
     "cap4d_b200_unet_num_params": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "cap4d_b200_unet_finalize": (c_int, [c_void_p]),
+    "cap4d_b200_unet_set_ref_views": (c_int, [c_void_p, c_int]),
     "cap4d_b200_unet_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "cap4d_b200_unet_forward": (
         c_int,

@@ -42,9 +42,11 @@ __global__ void input_pack_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---- output mix: mmdm_unet.py:77,122-125 ------------------------------------------------------
+// G > 0: h holds only the generated views (B*G images, view v >= R of group b at image b*G + v - R); the
+// reference views' outputs do not depend on h at all (ref_mask == 1 there).
 __global__ void output_mix_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ x,
                                   const float* __restrict__ z, const float* __restrict__ mask, int n_img, int cout,
-                                  int H, int W, float* __restrict__ out) {
+                                  int H, int W, int G, int V, int R, float* __restrict__ out) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -52,8 +54,27 @@ __global__ void output_mix_kernel(const float* __restrict__ h, int ldh, const fl
     const int c = static_cast<int>((i / (static_cast<size_t>(H) * W)) % cout);
     const size_t n = i / (static_cast<size_t>(H) * W * cout);
     const float m = mask[n * H * W + sp];
-    const float hv = h[(n * H * W + sp) * ldh + c];
+    float hv = 0.f;
+    if (G <= 0) {
+      hv = h[(n * H * W + sp) * ldh + c];
+    } else {
+      const int b = static_cast<int>(n) / V, v = static_cast<int>(n) % V;
+      if (v >= R) hv = h[((static_cast<size_t>(b) * G + (v - R)) * H * W + sp) * ldh + c];
+    }
     out[i] = (x[i] - z[i]) * m + hv * (m == 0.f ? 1.f : 0.f);
+  }
+}
+
+// ---- keep the generated views: dst image (b, g) = src image (b, R + g), per_img floats each -----------
+__global__ void gather_views_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int B, int V, int R,
+                                    size_t quads_per_img) {
+  const int G = V - R;
+  const size_t total = static_cast<size_t>(B) * G * quads_per_img;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t img = i / quads_per_img, off = i - img * quads_per_img;
+    const size_t b = img / G, g = img - b * G;
+    dst[i] = __ldg(src + (b * V + R + g) * quads_per_img + off);
   }
 }
 
@@ -262,9 +283,22 @@ cudaError_t launch_input_pack(const float* x, const float* z_input, const float*
 }
 
 cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
-                              int n_img, int cout, int H, int W, float* out, cudaStream_t stream) {
+                              int n_img, int cout, int H, int W, int G, int V, int R, float* out,
+                              cudaStream_t stream) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
-  output_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, x, z_input, ref_mask, n_img, cout, H, W, out);
+  output_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, x, z_input, ref_mask, n_img, cout, H, W, G, V, R,
+                                                              out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int R, size_t per_img, cudaStream_t stream) {
+  if (per_img % 4 != 0 || R < 0 || R >= V) {
+    set_error("gather_views: per-image size must be a multiple of 4 floats and 0 <= R < V");
+    return cudaErrorInvalidValue;
+  }
+  const size_t total = static_cast<size_t>(B) * (V - R) * (per_img / 4);
+  gather_views_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                                reinterpret_cast<float4*>(dst), B, V, R, per_img / 4);
   return cudaGetLastError();
 }
 

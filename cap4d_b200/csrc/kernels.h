@@ -116,9 +116,12 @@ cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* tr
 // [M][C1+C2] = (silu?)(gn(x)) and optionally a raw bf16 copy of x.
 // partial: scratch of groupnorm_partial_bytes(n_img): fp32 [n_img][GN_MAX_CHUNKS][32][2] + barrier counters.
 enum { GN_MAX_CHUNKS = 128 };
+// x2_G > 0: x1 / out hold B*x2_G images (the generated views) while x2 still holds B*x2_V images; image n
+// reads x2 image (n / x2_G) * x2_V + x2_R + n % x2_G.  n_img_layout: the image count `partial` was sized and
+// zeroed for when that is more than n_img (0 = n_img).
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int x2_G = 0, int x2_V = 0, int x2_R = 0, int n_img_layout = 0);
 size_t groupnorm_partial_bytes(int n_img);
 size_t groupnorm_sync_offset(int n_img);  // the bytes from here to the end must be zero before the first launch
 
@@ -137,7 +140,10 @@ cudaError_t launch_input_pack(const float* x, const float* z_input, const float*
                               cudaStream_t stream);
 // Output stage (mmdm_unet.py:118-125): eps = x_input*mask + h*(1-mask), NHWC(ld) -> [n_img][cout][H][W]
 cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
-                              int n_img, int cout, int H, int W, float* out, cudaStream_t stream);
+                              int n_img, int cout, int H, int W, int G, int V, int R, float* out,
+                              cudaStream_t stream);
+// dst image (b, g) = src image (b, R + g) for g < V - R: drops the R leading (reference) views of every group
+cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int R, size_t per_img, cudaStream_t stream);
 // fp32 NHWC -> bf16 NHWC, nearest 2x upsample
 cudaError_t launch_upsample2x_bf16(const float* x, int n_img, int H, int W, int C, bf16* out, cudaStream_t stream);
 // fp32 NHWC -> bf16 parity planes [4][n_img][H/2][W/2][C] (plane = (y&1)*2 + (x&1))

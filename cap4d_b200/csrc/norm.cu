@@ -76,11 +76,12 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img) {
   return g;
 }
 
+// row2 = row + x2_shift: the second source may hold more images than the first (see launch_groupnorm)
 __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2,
-                                          size_t row, int c) {
+                                          size_t row, size_t row2, int c) {
   // c is a multiple of 4 and C1 is a multiple of 4, so a quad never straddles the seam
   if (c < C1) return __ldg(reinterpret_cast<const float4*>(x1 + row * C1 + c));
-  return __ldg(reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1)));
+  return __ldg(reinterpret_cast<const float4*>(x2 + row2 * C2 + (c - C1)));
 }
 
 // ---- GroupNorm (+SiLU), one kernel ---------------------------------------------------------------
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256)
 gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
                 int rows_per_chunk, int n_chunks, float* __restrict__ partial, GnSync* __restrict__ sync,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int apply_silu,
-                bf16* __restrict__ out, bf16* __restrict__ raw_out) {
+                bf16* __restrict__ out, bf16* __restrict__ raw_out, int x2_G, int x2_V, int x2_R) {
   extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
   __shared__ double s_part[8][GN_GROUPS][2];
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -114,6 +115,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
   const size_t img_row = static_cast<size_t>(n) * hw;
+  const size_t img_row2 = (x2_G > 0) ? static_cast<size_t>((n / x2_G) * x2_V + x2_R + n % x2_G) * hw : img_row;
 
   // ---------------- phase 1: statistics of this chunk ----------------
   {
@@ -128,7 +130,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-        for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+        for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
@@ -142,7 +144,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     for (; r < r1; r += TY) {
 #pragma unroll
       for (int qi = 0; qi < NQI; ++qi) {
-        const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4);
+        const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4);
         sum[qi][0] += v.x; sq[qi][0] = fmaf(v.x, v.x, sq[qi][0]);
         sum[qi][1] += v.y; sq[qi][1] = fmaf(v.y, v.y, sq[qi][1]);
         sum[qi][2] += v.z; sq[qi][2] = fmaf(v.z, v.z, sq[qi][2]);
@@ -251,7 +253,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, (tx + qi * TX) * 4);
+      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
@@ -259,7 +261,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
   }
   for (; r < r1; r += TY) {
 #pragma unroll
-    for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, (tx + qi * TX) * 4));
+    for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4));
   }
   // ---------------- the last chunk of the image resets its counters for the next launch ----------------
   __syncthreads();
@@ -330,14 +332,15 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
 template <int NQI>
 cudaError_t launch_gn_t(const GnGeom& g, const float* x1, int C1, const float* x2, int C2, int n_img, int hw,
                         const float* gamma, const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out,
-                        float* partial, cudaStream_t stream) {
+                        float* partial, cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_layout) {
   constexpr int UNROLL = (NQI >= 4) ? 2 : 4;
   const int C = C1 + C2;
   dim3 grid(g.n_chunks, n_img), block(g.TX, g.TY);
-  GnSync* sync = reinterpret_cast<GnSync*>(partial + static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2);
+  // the barrier counters sit behind the partials of the image count the scratch was laid out (and zeroed) for
+  GnSync* sync = reinterpret_cast<GnSync*>(partial + static_cast<size_t>(n_layout) * GN_MAX_CHUNKS * GN_GROUPS * 2);
   gn_fused_kernel<NQI, UNROLL><<<grid, block, static_cast<size_t>(2) * C * g.TY * sizeof(float), stream>>>(
       x1, x2, C1, C2, hw, g.cpg, g.rows_per_chunk, g.n_chunks, partial, sync, gamma, beta, eps, apply_silu, out,
-      raw_out);
+      raw_out, x2_G, x2_V, x2_R);
   return cudaGetLastError();
 }
 
@@ -353,8 +356,9 @@ size_t groupnorm_sync_offset(int n_img) { return static_cast<size_t>(n_img) * GN
 
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_img_layout) {
   const int C = C1 + C2;
+  const int n_layout = n_img_layout > 0 ? n_img_layout : n_img;
   if (C % GN_GROUPS != 0 || C1 % 4 != 0 || C2 % 4 != 0) {
     set_error("groupnorm: channels must be a multiple of 32 (each source a multiple of 4)");
     return cudaErrorInvalidValue;
@@ -365,7 +369,8 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
     return cudaErrorInvalidValue;
   }
 #define CAP4D_GN_CASE(N) \
-  return launch_gn_t<N>(g, x1, C1, x2, C2, n_img, hw, gamma, beta, eps, apply_silu, out, raw_out, partial, stream)
+  return launch_gn_t<N>(g, x1, C1, x2, C2, n_img, hw, gamma, beta, eps, apply_silu, out, raw_out, partial, stream, \
+                        x2_G, x2_V, x2_R, n_layout)
   if (g.nqi == 1) CAP4D_GN_CASE(1);
   if (g.nqi == 2) CAP4D_GN_CASE(2);
   CAP4D_GN_CASE(4);

@@ -181,11 +181,14 @@ struct Unet {
   // plan
   std::vector<Op> ops;
   IoPtrs io;
-  int pB = 0, pV = 0, pH = 0, pW = 0;
+  int pB = 0, pV = 0, pH = 0, pW = 0, pR = 0;
+  // Caller's promise (cap4d_b200_unet_set_ref_views): the first ref_views views of every group are reference
+  // views (ref_mask == 1), so their outputs are x - z_input whatever the network computes for them.
+  int ref_views = 0;
   void* p_ws = nullptr;
   size_t p_ws_bytes = 0;
   struct CachedPlan {
-    int B, V, H, W;
+    int B, V, H, W, R;
     void* ws;
     size_t ws_bytes;
     std::vector<Op> ops;
@@ -589,8 +592,11 @@ struct Unet {
     Arena arena;
     bool dry = true;
     uint8_t* base = nullptr;
-    int n_img = 0, V = 0;
-    float* emb_all = nullptr;
+    int n_img = 0, V = 0;      // n_img: images the layers being planned work on (B*V, or B*G once compact)
+    int B = 0, R = 0, G = 0;   // R > 0: drop the R leading views of every group after the last cross-view layer
+    bool compact = false;      // the current activations hold only the generated views
+    float* emb_all = nullptr;  // rows of the images being planned (all views, or the gathered generated views)
+    float* emb_gen = nullptr;
     float* gn_partial = nullptr;
     std::vector<Op>* ops = nullptr;
     template <typename T>
@@ -634,13 +640,16 @@ struct Unet {
     bf16* pr = raw_out ? c.ptr<bf16>(*raw_out) : nullptr;
     float* partial = c.gn_partial;
     const int n_img = c.n_img;
+    // once compact, x1 holds the generated views only while a skip tensor x2 still holds every view
+    const int x2G = (c.compact && x2 != nullptr) ? c.G : 0, x2V = c.V, x2R = c.R, n_layout = c.B * c.V;
     Op op;
     op.cls = CLS_GN;
     op.launches = 1;
     op.flops = 0;
     op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
     op.run = [=](cudaStream_t s) {
-      return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s);
+      return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s, x2G, x2V, x2R,
+                              n_layout);
     };
     c.ops->push_back(op);
     return true;
@@ -814,7 +823,36 @@ struct Unet {
     return true;
   }
 
-  bool plan_block(PlanCtx& c, const Block& blk, Buf x, const Buf* skip, int* H, int* W, Buf* out) {
+  // After the last cross-view ("3d") transformer every remaining layer treats the views independently,
+  // and the reference views' outputs are discarded by the output mix (mmdm_unet.py:122-125: x - z_input
+  // where ref_mask == 1).  With R promised reference views the rest of the network therefore runs on the
+  // generated views only: one gather of the activations here, skip tensors are read in place by GroupNorm.
+  bool plan_compact(PlanCtx& c, Buf* cur, int hw) {
+    const int C = cur->C;
+    Buf dst = c.alloc(c.B * c.G * hw, C, 4);
+    if (!c.dry) {
+      const float* src = c.ptr<float>(*cur);
+      float* d = c.ptr<float>(dst);
+      const int B = c.B, V = c.V, R = c.R;
+      const size_t per_img = static_cast<size_t>(hw) * C;
+      Op op;
+      op.cls = CLS_OTHER;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(dst.M) * C * 8;
+      op.run = [=](cudaStream_t s) { return launch_gather_views(src, d, B, V, R, per_img, s); };
+      c.ops->push_back(op);
+    }
+    c.release(*cur);
+    *cur = dst;
+    c.compact = true;
+    c.n_img = c.B * c.G;
+    c.emb_all = c.emb_gen;
+    return true;
+  }
+
+  bool plan_block(PlanCtx& c, const Block& blk, Buf x, const Buf* skip, int* H, int* W, Buf* out,
+                  int compact_after = -1) {
     // x is owned by this call (released once consumed); skip is owned by the caller
     Buf cur = x;
     for (size_t li = 0; li < blk.size(); ++li) {
@@ -840,16 +878,39 @@ struct Unet {
       }
       c.release(cur);
       cur = nxt;
+      if (static_cast<int>(li) == compact_after && !plan_compact(c, &cur, *H * *W)) return false;
     }
     *out = cur;
     return true;
   }
 
-  bool build_plan(PlanCtx& c, int B, int V, int H, int W) {
+  // the (block, layer) of the up path's last cross-view transformer; false if a later stage has none
+  bool last_3d_in_up_path(int* block, int* layer) const {
+    *block = *layer = -1;
+    for (size_t bi = 0; bi < output_blocks.size(); ++bi)
+      for (size_t li = 0; li < output_blocks[bi].size(); ++li)
+        if (output_blocks[bi][li].kind == L_TF && tf[output_blocks[bi][li].idx].is3d) {
+          *block = static_cast<int>(bi);
+          *layer = static_cast<int>(li);
+        }
+    return *block >= 0;
+  }
+
+  bool build_plan(PlanCtx& c, int B, int V, int H, int W, int R) {
     const int mc = cfg.model_channels;
     const int n_img = B * V;
     c.n_img = n_img;
     c.V = V;
+    c.B = B;
+    int cb = -1, cl = -1;
+    if (R < 0 || R >= V) {
+      set_error("n_ref_views must be in [0, V)");
+      return false;
+    }
+    if (R > 0 && last_3d_in_up_path(&cb, &cl)) {
+      c.R = R;
+      c.G = V - R;
+    }
     const int down_factor = 1 << (cfg.n_levels - 1);
     if (H % down_factor != 0 || W % down_factor != 0) {
       set_error("H and W must be divisible by 2^(n_levels-1)");
@@ -861,12 +922,15 @@ struct Unet {
     te_scratch.bytes = time_embed_scratch_bytes(n_img, mc, emb_ch);
     te_scratch.off = c.arena.alloc(te_scratch.bytes);
     te_scratch.valid = true;
+    Buf embg;
+    if (c.R > 0) embg = c.alloc(B * c.G, n_all, 4);
     Buf gnp;
     gnp.bytes = groupnorm_partial_bytes(n_img);
     gnp.off = c.arena.alloc(gnp.bytes);
     gnp.valid = true;
     if (!c.dry) {
       c.emb_all = c.ptr<float>(emb);
+      c.emb_gen = (c.R > 0) ? c.ptr<float>(embg) : nullptr;
       c.gn_partial = c.ptr<float>(gnp);
       // the GroupNorm kernel's per-image barrier counters start at zero (it re-zeroes them itself)
       CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(n_img), 0, gnp.bytes - groupnorm_sync_offset(n_img)));
@@ -905,6 +969,17 @@ struct Unet {
           return launch_time_embed(iop->t, n_img, mc, ech, w1, b1, w2, b2, wa, ba, nall, scratch, embp, s);
         };
         c.ops->push_back(op);
+        if (c.R > 0) {  // the generated views' rows, for the ResBlocks planned after the compaction
+          float* eg = c.emb_gen;
+          const int Bv = B, Vv = V, Rv = c.R;
+          Op og;
+          og.cls = CLS_OTHER;
+          og.launches = 1;
+          og.flops = 0;
+          og.bytes = static_cast<double>(B) * c.G * nall * 8;
+          og.run = [=](cudaStream_t s) { return launch_gather_views(embp, eg, Bv, Vv, Rv, nall, s); };
+          c.ops->push_back(og);
+        }
       }
       GemmPlan p;
       if (!make_gemm_plan(&p, pa0, M0, kp, nullptr, 0, w_in, mc, OUT_F32, c.ptr<float>(h), mc, b_in, nullptr, 1, 0,
@@ -940,18 +1015,20 @@ struct Unet {
       Buf skip = hs.back();
       hs.pop_back();
       Buf nxt;
-      if (!plan_block(c, output_blocks[bi], cur, &skip, &curH, &curW, &nxt)) return false;
+      const int compact_after = (c.R > 0 && static_cast<int>(bi) == cb) ? cl : -1;
+      if (!plan_block(c, output_blocks[bi], cur, &skip, &curH, &curW, &nxt, compact_after)) return false;
       c.release(skip);
       cur = nxt;
     }
-    // ---- out
-    Buf a = c.alloc(M0, mc, 2);
+    // ---- out (on the generated views only once compact)
+    const int Mo = c.n_img * H * W;
+    Buf a = c.alloc(Mo, mc, 2);
     if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr)) return false;
     c.release(cur);
-    Buf o32 = c.alloc(M0, 32, 4);
+    Buf o32 = c.alloc(Mo, 32, 4);
     if (!c.dry) {
       GemmPlan p;
-      ConvGeom g{n_img, H, W, 9, 1};
+      ConvGeom g{c.n_img, H, W, 9, 1};
       if (!make_conv_plan(&p, c.ptr<bf16>(a), g, mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
                           nullptr, 1, 0, nullptr, 0))
         return false;
@@ -959,13 +1036,14 @@ struct Unet {
       IoPtrs* iop = &io;
       const float* po = c.ptr<float>(o32);
       const int cout = cfg.out_channels;
+      const int mixG = c.compact ? c.G : 0, mixR = c.R;
       Op op;
       op.cls = CLS_OTHER;
       op.launches = 1;
       op.flops = 0;
       op.bytes = static_cast<double>(M0) * cout * 16;
       op.run = [=](cudaStream_t s) {
-        return launch_output_mix(po, 32, iop->x, iop->z, iop->mask, n_img, cout, H, W, iop->out, s);
+        return launch_output_mix(po, 32, iop->x, iop->z, iop->mask, n_img, cout, H, W, mixG, V, mixR, iop->out, s);
       };
       c.ops->push_back(op);
     }
@@ -979,7 +1057,7 @@ struct Unet {
     c.dry = true;
     std::vector<Op> dummy;
     c.ops = &dummy;
-    if (!build_plan(c, B, V, H, W)) return false;
+    if (!build_plan(c, B, V, H, W, ref_views)) return false;
     *bytes = c.arena.peak + 1024;
     return true;
   }
@@ -989,21 +1067,23 @@ struct Unet {
       set_error("cap4d_b200_unet_finalize has not been called");
       return false;
     }
-    if (B == pB && V == pV && H == pH && W == pW && ws == p_ws && ws_bytes == p_ws_bytes && !ops.empty()) return true;
+    const int R = ref_views;
+    if (B == pB && V == pV && H == pH && W == pW && R == pR && ws == p_ws && ws_bytes == p_ws_bytes && !ops.empty())
+      return true;
     // park the current plan and look for a cached one (a sampler alternates between at most a few batch
     // shapes, e.g. 4 groups per call and a 3-group remainder; each shape has its own workspace)
     if (!ops.empty()) {
       if (cache.size() >= 4) cache.erase(cache.begin());
       cache.emplace_back();
       CachedPlan& cp = cache.back();
-      cp.B = pB, cp.V = pV, cp.H = pH, cp.W = pW, cp.ws = p_ws, cp.ws_bytes = p_ws_bytes;
+      cp.B = pB, cp.V = pV, cp.H = pH, cp.W = pW, cp.R = pR, cp.ws = p_ws, cp.ws_bytes = p_ws_bytes;
       cp.ops.swap(ops);
     }
     for (size_t i = 0; i < cache.size(); ++i) {
       CachedPlan& cp = cache[i];
-      if (cp.B == B && cp.V == V && cp.H == H && cp.W == W && cp.ws == ws && cp.ws_bytes == ws_bytes) {
+      if (cp.B == B && cp.V == V && cp.H == H && cp.W == W && cp.R == R && cp.ws == ws && cp.ws_bytes == ws_bytes) {
         ops.swap(cp.ops);
-        pB = B, pV = V, pH = H, pW = W, p_ws = ws, p_ws_bytes = ws_bytes;
+        pB = B, pV = V, pH = H, pW = W, pR = R, p_ws = ws, p_ws_bytes = ws_bytes;
         cache.erase(cache.begin() + i);
         return true;
       }
@@ -1019,10 +1099,11 @@ struct Unet {
     c.dry = false;
     c.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
     c.ops = &ops;
-    if (!build_plan(c, B, V, H, W)) {
+    if (!build_plan(c, B, V, H, W, R)) {
       ops.clear();
       return false;
     }
+    pR = R;
     pB = B;
     pV = V;
     pH = H;
@@ -1242,6 +1323,16 @@ static int forward_impl(void* handle, const float* x, const int64_t* timesteps, 
   return u->forward(io, B, V, H, W, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), timed, class_ms)
              ? 0
              : 6;
+}
+
+int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || n_ref_views < 0) {
+    set_error("set_ref_views: null handle or negative count");
+    return 1;
+  }
+  u->ref_views = n_ref_views;
+  return 0;
 }
 
 int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timesteps, const float* z_input,

@@ -70,8 +70,10 @@ class _CudaBackend:
         self.device = unet.device
         self._lib = _lib.load()
 
-    def eps(self, x_in, t_in, control):
-        return self.unet(x_in, timesteps=t_in, context=None, control=control)
+    def eps(self, x_in, t_in, control, n_ref_views=0):
+        # the groups are built as cat([ref, gen], dim=1): the first R views are reference views, and only the
+        # generated views' noise prediction is consumed (sampler.py:207-213)
+        return self.unet(x_in, timesteps=t_in, context=None, control=control, n_ref_views=n_ref_views)
 
     def cfg_ddim_update(self, latents, eps, gen_idx, n, V, R, chw, cfg_scale, x_f, e_f):
         stream = torch.cuda.current_stream(self.device)
@@ -183,7 +185,7 @@ class B200StochasticIOSampler:
             x_in = torch.cat([rc["z_input"][ref_idx], latents[gen_idx]], dim=1)
             x_in = torch.cat([x_in, x_in], dim=0)
             t_in = torch.full((2 * n, V), int(step), device=dev, dtype=torch.long)
-            eps = self.backend.eps(x_in, t_in, control)
+            eps = self.backend.eps(x_in, t_in, control, n_ref_views=R)
             self.unet_calls += 1
             self.backend.cfg_ddim_update(latents, eps, gen_idx, n, V, R, st.chw, st.cfg_scale, x_f, e_f)
 

@@ -155,8 +155,9 @@ class B200MMDMUnet(torch.nn.Module):
         except Exception:
             pass
 
-    def _workspace(self, B, V, H, W) -> torch.Tensor:
-        key = (B, V, H, W)
+    def _workspace(self, B, V, H, W, R=0) -> torch.Tensor:
+        _lib.check(self._lib.cap4d_b200_unet_set_ref_views(self._handle, int(R)), "set_ref_views")
+        key = (B, V, H, W, R)
         ws = self._ws.get(key)
         if ws is None:
             if len(self._ws) >= 4:  # the library caches 4 plans as well
@@ -195,13 +196,20 @@ class B200MMDMUnet(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, control=None, **kwargs):
+        """Reference signature (mmdm_unet.py:67).  Extra keyword `n_ref_views=R` (not in the reference; other
+        unknown keywords such as only_mid_control are swallowed like there): the caller promises that the
+        first R views of every group are reference views (ref_mask == 1), which lets the executor skip them
+        once no later layer mixes views.  The returned tensor is the same either way."""
         assert context is None  # mmdm_unet.py:85
         xs, t, z, m, p = self._prep(x, timesteps, control)
         B, V, C, H, W = xs.shape
+        R = int(kwargs.get("n_ref_views") or 0)
+        if not 0 <= R < V:
+            raise ValueError("n_ref_views must be in [0, V)")
         out = torch.empty((B, V, self.config["out_channels"], H, W), dtype=torch.float32, device=self._device)
         self._calls += 1
         with torch.cuda.device(self._device):
-            ws = self._workspace(B, V, H, W)
+            ws = self._workspace(B, V, H, W, R)
             stream = torch.cuda.current_stream(self._device).cuda_stream
             if self.record_every and self._calls % self.record_every == 0:
                 _lib.check(
@@ -227,14 +235,14 @@ class B200MMDMUnet(torch.nn.Module):
         return {c: float(ms[i]) for i, c in enumerate(_lib.CLASS_NAMES)}, n.value
 
     @torch.no_grad()
-    def forward_timed(self, x, timesteps, control):
+    def forward_timed(self, x, timesteps, control, n_ref_views=0):
         """One forward with CUDA events around every launch; returns (out, {class: ms})."""
         xs, t, z, m, p = self._prep(x, timesteps, control)
         B, V, C, H, W = xs.shape
         out = torch.empty((B, V, self.config["out_channels"], H, W), dtype=torch.float32, device=self._device)
         ms = (ctypes.c_float * _lib.N_CLASSES)()
         with torch.cuda.device(self._device):
-            ws = self._workspace(B, V, H, W)
+            ws = self._workspace(B, V, H, W, int(n_ref_views))
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(
                 self._lib.cap4d_b200_unet_forward_timed(self._handle, xs.data_ptr(), t.data_ptr(), z.data_ptr(),

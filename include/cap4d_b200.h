@@ -63,6 +63,14 @@ int cap4d_b200_unet_param_info(void* handle, int index, char* name, int name_cap
  * layouts).  Fails if any parameter of the topology was not loaded. */
 int cap4d_b200_unet_finalize(void* handle);
 
+/* Optional promise about the batches that follow: the first n_ref_views views of every group are
+ * reference views, i.e. ref_mask == 1 on them, as StochasticIOSampler builds its groups
+ * (cap4d/mmdm/sampler.py:171-195: torch.cat([ref, gen], dim=1)).  Their outputs are x - z_input whatever
+ * the network computes (mmdm_unet.py:122-125), so after the last cross-view attention layer the executor
+ * keeps only the generated views.  0 (the default) computes every view like the reference.  Affects
+ * workspace_bytes and forward calls made after it; outputs are unchanged. */
+int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views);
+
 /* Scratch needed by one forward at this shape (caller owns the buffer; >= 1024 B aligned). */
 int cap4d_b200_unet_workspace_bytes(void* handle, int B, int V, int H, int W, size_t* bytes);
 

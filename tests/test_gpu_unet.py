@@ -75,6 +75,29 @@ def test_unet_matches_oracle(cuda_device, tiny_unets, B, V, H, W, R, tstep):
     assert err < EPS_TOL
 
 
+@pytest.mark.parametrize("B,V,H,W,R", [(2, 4, 16, 16, 1), (4, 4, 16, 16, 2), (2, 6, 8, 8, 3), (2, 4, 16, 32, 1)])
+def test_unet_reference_view_hint(cuda_device, tiny_unets, B, V, H, W, R):
+    """n_ref_views=R lets the executor drop the reference views after the last cross-view layer; the
+    returned tensor must not change: reference views exactly x - z_input, generated views equal to the full
+    computation up to the GroupNorm partial-sum grouping (which depends on the image count)."""
+    unet, sd = tiny_unets(0)
+    x, t, ctrl = O.make_inputs(O.TINY_CONFIG, B=B, V=V, H=H, W=W, R=R, seed=7 * B + R, timestep=333)
+    kw = dict(timesteps=t.to(cuda_device), context=None, control=_to(ctrl, cuda_device))
+    full = unet(x.to(cuda_device), **kw)
+    n_full = unet.num_launches()
+    hint = unet(x.to(cuda_device), n_ref_views=R, **kw)
+    assert unet.num_launches() == n_full + 2  # gather of the activations and of the embedding rows
+    assert torch.equal(hint[:, :R], full[:, :R])
+    assert O.max_rel_err(hint[:, R:].cpu(), full[:, R:].cpu()) < 2e-5
+    ref = O.unet_forward(sd, O.TINY_CONFIG, x, t, ctrl)
+    assert torch.equal(hint[:, :R].cpu(), ref[:, :R])
+    assert O.max_rel_err(hint[:, R:].cpu(), ref[:, R:]) < EPS_TOL
+    again = unet(x.to(cuda_device), n_ref_views=R, **kw)
+    assert torch.equal(again, hint)
+    with pytest.raises(ValueError):
+        unet(x.to(cuda_device), n_ref_views=V, **kw)
+
+
 def test_unet_per_view_timesteps_and_determinism(cuda_device, tiny_unets):
     # the API allows a different timestep per view (timesteps: [B, V]); the sampler never does
     unet, sd = tiny_unets(0)
@@ -114,6 +137,13 @@ def test_unet_production_config(cuda_device):
     total = sum(s["flops"] for s in stats.values())
     # 14.034 TFLOP per call; ours counts padded K (input stage) and N (out conv), so slightly more
     assert 14.0e12 < total < 14.3e12, total
+    # the sampler's call: the reference view is dropped for the level-0 up path (1/8 of ~23 % of the FLOPs)
+    yh = unet(xd, timesteps=td, context=None, control=cd, n_ref_views=1)
+    assert torch.equal(yh[:, :1], ref[:, :1])
+    assert O.max_rel_err(yh[:, 1:].cpu(), ref[:, 1:].cpu()) < EPS_TOL
+    total_h = sum(s["flops"] for s in unet.class_stats().values())
+    print(f"production with n_ref_views=1: {total_h / 1e12:.3f} TFLOP per call ({total_h / total:.3f} of the full pass)")
+    assert 0.96 < total_h / total < 0.98
 
 
 @pytest.mark.parametrize("name,gpc", [("sampler_r1", 1), ("sampler_r1", 3), ("sampler_r2", 2)])

@@ -124,7 +124,8 @@ class _TorchBackend:
         self.sd, self.cfg = sd, cfg
         self.device = torch.device("cpu")
 
-    def eps(self, x_in, t_in, control):
+    def eps(self, x_in, t_in, control, n_ref_views=0):
+        assert float(control["ref_mask"][:, :n_ref_views].min()) == 1.0  # the promise the product path relies on
         return O.unet_forward(self.sd, self.cfg, x_in, t_in, control)
 
     def cfg_ddim_update(self, latents, eps, gen_idx, n, V, R, chw, cfg_scale, x_f, e_f):
