@@ -175,6 +175,18 @@ def run_reference(args, rank):
 # =============================================================================================
 # B200 arm
 # =============================================================================================
+def _gemm_traffic(gpc):
+    """DRAM bytes per gemm_tc_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    launches of one U-Net call) from the committed ncu capture of the same batch shape; None if there is none."""
+    path = os.path.join(ROOT, "profiles", f"r01d_traffic_g{gpc}.json")
+    try:
+        with open(path) as f:
+            k = json.load(f)["kernels"]["gemm_tc_kernel"]
+        return k["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,7 +338,9 @@ def main():
             "roofline": {
                 "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": _gemm_traffic(gpc)[0],
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
+                                "GEMM launches of one U-Net call)", "traffic_source": _gemm_traffic(gpc)[1],
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "how": f"CUDA events around every launch of {n_rec} of {calls_timed} U-Net calls inside the timed region",
             },

@@ -23,7 +23,10 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--hw", type=int, default=64)
+    ap.add_argument("--ref-views", type=int, default=1,
+                    help="n_ref_views promise passed with every call, as the sampler does (0 = compute every view)")
     args = ap.parse_args()
+    R = args.ref_views
     dev = torch.device("cuda:0")
     unet = B200MMDMUnet.random_init(MMDM_UNET_CONFIG, seed=0, device=dev)
     B, V, H = 2 * args.groups, 8, args.hw
@@ -35,28 +38,28 @@ def main():
     ctrl["ref_mask"][:, :1] = 1.0
     t = torch.full((B, V), 501, device=dev, dtype=torch.long)
     for _ in range(args.warm):
-        unet(x, timesteps=t, control=ctrl)
+        unet(x, timesteps=t, control=ctrl, n_ref_views=R)
     torch.cuda.synchronize()
     if args.ncu:
         torch.cuda.profiler.start()
-        unet(x, timesteps=t, control=ctrl)
+        unet(x, timesteps=t, control=ctrl, n_ref_views=R)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.iters):
-        unet(x, timesteps=t, control=ctrl)
+        unet(x, timesteps=t, control=ctrl, n_ref_views=R)
     e1.record()
     torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1) / args.iters
     acc = None
     for _ in range(args.iters):
-        _, ms = unet.forward_timed(x, t, ctrl)
+        _, ms = unet.forward_timed(x, t, ctrl, n_ref_views=R)
         acc = ms if acc is None else {k: acc[k] + ms[k] for k in ms}
     ms = {k: v / args.iters for k, v in acc.items()}
     stats = unet.class_stats()
-    out = {"shape": [B, V, H, H], "forward_ms_back_to_back": total_ms, "forward_ms_sum_of_launches": sum(ms.values()),
+    out = {"shape": [B, V, H, H], "n_ref_views": R, "forward_ms_back_to_back": total_ms, "forward_ms_sum_of_launches": sum(ms.values()),
            "launches": unet.num_launches(), "classes": {}}
     flops_total = sum(s["flops"] for s in stats.values())
     out["tflops_total"] = flops_total / 1e12
