@@ -168,6 +168,38 @@ def test_sampler_matches_reference_fixture(cuda_device, name, gpc):
     assert p >= 40.0
 
 
+def test_sampler_production_config(cuda_device):
+    """The shipped architecture (cap4d_mmdm_final.yaml) through the whole sampler: 1 reference + 14 generated
+    views at 64x64, S = 5 DDIM steps, cfg 2.0 - the single_ref.yaml settings with fewer views and steps.
+    Checker: the oracle's sampler with its U-Net evaluated on the GPU in fp32 (TF32 off), same RNG streams."""
+    from cap4d_b200 import B200MMDMUnet, B200MMLDM, B200StochasticIOSampler
+
+    cfg = O.PRODUCTION_CONFIG
+    sd = O.init_state_dict(cfg, seed=0)
+    H = W = 64
+    rc, ru, gc, gu = O.make_sampler_conditioning(cfg, 1, 14, H, W, seed=5)
+    kw = dict(S=5, ref_cond=rc, ref_uncond=ru, gen_cond=gc, gen_uncond=gu, latent_shape=(4, H, W), V=8, R_max=4,
+              cfg_scale=2.0)
+    model = B200MMLDM(B200MMDMUnet(cfg, sd, device=cuda_device))
+    torch.manual_seed(124)
+    np.random.seed(124)
+    z = B200StochasticIOSampler(model, groups_per_call=2).sample(**kw)
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd_dev = {k: v.to(cuda_device) for k, v in sd.items()}
+
+    def eps_fn(x, t, control):
+        return O.unet_forward(sd_dev, cfg, x.to(cuda_device), t.to(cuda_device), _to(control, cuda_device)).cpu()
+
+    torch.manual_seed(124)
+    np.random.seed(124)
+    ref = O.stochastic_io_sample(eps_fn, model.alphas_cumprod.cpu().numpy(), **kw)
+    p = O.psnr(z, ref)
+    print(f"production sampler, 14 views, S=5: PSNR {p:.1f} dB max-rel {O.max_rel_err(z, ref):.3e}")
+    assert z.shape == (14, 4, H, W) and p >= 40.0
+
+
 def test_reference_call_convention(cuda_device, tiny_unets):
     """MMLDM.apply_model(x, t, {'c_concat': [control]}) and the extra only_mid_control kwarg
     (cap4d/mmdm/mmdm.py:113-124, sampler.py:201-205)."""
