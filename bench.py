@@ -194,6 +194,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-gen", type=int, default=840)
+    ap.add_argument("--workload", default="single_ref", choices=["single_ref", "multi_ref"],
+                    help="single_ref.yaml (1 reference, 7 generated views per group: the headline) or multi_ref.yaml "
+                         "(10 references, 4 drawn per group and step, 4 generated views per group)")
     ap.add_argument("--groups-per-call", type=int, default=5,
                     help="upper bound; the largest divisor of the groups per rank not above it is used")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -221,14 +224,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), max(1, args.steps)
     n_gen = args.n_gen
-    assert n_gen % 7 == 0
-    groups_per_rank = (n_gen // 7 + world - 1) // world
+    n_all_ref = 1 if args.workload == "single_ref" else 10     # multi_ref.yaml: n_all_ref 10, R_max 4
+    G = V - min(n_all_ref, 4)                                   # generated views per group
+    assert n_gen % G == 0
+    groups_per_rank = (n_gen // G + world - 1) // world
     # every U-Net call of the timed region has the same batch shape: pick a divisor of the rank's share
     gpc = max(d for d in range(1, max(1, args.groups_per_call) + 1) if groups_per_rank % d == 0)
 
     unet = B200MMDMUnet.random_init(MMDM_UNET_CONFIG, seed=0, device=dev)
     model = B200MMLDM(unet)
-    rc, ru, gc, gu = synthetic_conditioning(1, n_gen, seed=1, pin=True)
+    rc, ru, gc, gu = synthetic_conditioning(n_all_ref, n_gen, seed=1, pin=True)
 
     def barrier():
         if world > 1:
@@ -321,7 +326,8 @@ def main():
             "dtype": "bf16",
             "data": "synthetic",
             "config": {
-                "workload": "single_ref.yaml: 1 ref + 7 gen views per group (V=8), 64x64 latents, "
+                "workload": f"{args.workload}.yaml: {V - G} ref + {G} gen views per group (V=8"
+                            f"{', 4 of 10 references drawn per group and step' if n_all_ref > 1 else ''}), 64x64 latents, "
                             "cap4d_mmdm_final U-Net (815.5M params), random-init",
                 "n_gen": n_gen, "S": S_TOTAL, "cfg_scale": CFG_SCALE, "groups_per_call": gpc,
                 "unet_calls_per_step_per_rank": calls_timed // K,
@@ -357,7 +363,7 @@ def main():
             times, cores = cpu_unet_seconds(1, 0, budget_s=120.0)
             t_half = float(np.median(times))
             line["cpu_baseline"] = {
-                "value": 7.0 / (2.0 * t_half * S_TOTAL), "unit": "views/s", "cores": cores, "kind": "port",
+                "value": float(G) / (2.0 * t_half * S_TOTAL), "unit": "views/s", "cores": cores, "kind": "port",
                 "sample": f"one oracle U-Net forward of a conditional half-batch (B=1, V=8, 64x64): {t_half:.1f} s; "
                           "a group's CFG pair = 2 halves; extrapolated linearly in groups x steps",
             }
