@@ -136,24 +136,63 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n
   if ((dim & 1) && k == 0) out[static_cast<size_t>(n) * dim + dim - 1] = 0.f;
 }
 
-// ---- skinny fp32 linear: out[n][j] = act(sum_k W[j][k] in[n][k] + b[j]), n <= a few dozen -------
+// ---- distinct timesteps: the embedding MLP is a pure function of t, and inside the sampler every view of
+// a step carries the same t (sampler.py:126), so it is evaluated once per DISTINCT value and copied.
+// rep[r] = first row with the same timestep as row r; uniq = {count, rows with rep[r] == r ...}
+__global__ void timestep_unique_kernel(const long long* __restrict__ t, int n, int* __restrict__ rep,
+                                       int* __restrict__ uniq) {
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    int first = r;
+    for (int q = 0; q < r; ++q)
+      if (t[q] == t[r]) {
+        first = q;
+        break;
+      }
+    rep[r] = first;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int r = 0; r < n; ++r)
+      if (rep[r] == r) uniq[1 + cnt++] = r;
+    uniq[0] = cnt;
+  }
+}
+
+__global__ void broadcast_rows_kernel(float* __restrict__ out, int n_rows, int n_cols, const int* __restrict__ rep) {
+  const size_t total = static_cast<size_t>(n_rows) * n_cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n_cols);
+    const int src = rep[r];
+    if (src != r) out[i] = out[static_cast<size_t>(src) * n_cols + (i - static_cast<size_t>(r) * n_cols)];
+  }
+}
+
+// ---- skinny fp32 linear: out[n][j] = act(sum_k W[j][k] in[n][k] + b[j]) for the rows listed in uniq -------
 // one warp per output column j; lanes split K; 16 rows of `in` per pass
-__global__ void skinny_linear_kernel(const float* __restrict__ in, int n_rows, int K, const float* __restrict__ Wm,
-                                     const float* __restrict__ bias, int n_out, int silu_out, float* __restrict__ out) {
+__global__ void skinny_linear_kernel(const float* __restrict__ in, const int* __restrict__ uniq, int K,
+                                     const float* __restrict__ Wm, const float* __restrict__ bias, int n_out,
+                                     int silu_out, float* __restrict__ out) {
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= n_out) return;
+  const int n_rows = uniq[0];
   const float* wr = Wm + static_cast<size_t>(j) * K;
   for (int r0 = 0; r0 < n_rows; r0 += 16) {
     float acc[16];
+    int row[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+    for (int r = 0; r < 16; ++r) {
+      acc[r] = 0.f;
+      row[r] = (r0 + r < n_rows) ? uniq[1 + r0 + r] : -1;
+    }
     for (int k = lane * 4; k < K; k += 128) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        if (r0 + r < n_rows) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r0 + r) * K + k));
+        if (row[r] >= 0) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(row[r]) * K + k));
           acc[r] += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
         }
       }
@@ -163,10 +202,10 @@ __global__ void skinny_linear_kernel(const float* __restrict__ in, int n_rows, i
       float v = acc[r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && r0 + r < n_rows) {
+      if (lane == 0 && row[r] >= 0) {
         v += bias[j];
         if (silu_out) v = v / (1.0f + expf(-v));
-        out[static_cast<size_t>(r0 + r) * n_out + j] = v;
+        out[static_cast<size_t>(row[r]) * n_out + j] = v;
       }
     }
   }
@@ -315,8 +354,8 @@ cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, in
   return cudaGetLastError();
 }
 
-size_t time_embed_scratch_bytes(int n_img, int model_ch, int emb_ch) {
-  return static_cast<size_t>(n_img) * (model_ch + 2 * emb_ch) * sizeof(float);
+size_t time_embed_scratch_bytes(int n_img, int model_ch, int emb_ch) {  // temb | h1 | silu(emb) | rep | uniq
+  return static_cast<size_t>(n_img) * (model_ch + 2 * emb_ch) * sizeof(float) + (2 * static_cast<size_t>(n_img) + 4) * sizeof(int);
 }
 
 cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int emb_ch, const float* w1,
@@ -329,14 +368,18 @@ cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int e
   float* temb = scratch;
   float* h1 = temb + static_cast<size_t>(n_img) * model_ch;
   float* se = h1 + static_cast<size_t>(n_img) * emb_ch;
+  int* rep = reinterpret_cast<int*>(se + static_cast<size_t>(n_img) * emb_ch);
+  int* uniq = rep + n_img;
   const int half = model_ch / 2;
+  timestep_unique_kernel<<<1, 256, 0, stream>>>(t, n_img, rep, uniq);
   timestep_embedding_kernel<<<(n_img * half + 127) / 128, 128, 0, stream>>>(t, n_img, model_ch, temb);
   const int wpb = 8;
   // time_embed: Linear -> SiLU -> Linear (openaimodel.py:528-533); every consumer applies SiLU first
   // (ResBlock.emb_layers, openaimodel.py:203-209), so silu(emb) is what is kept.
-  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(temb, n_img, model_ch, w1, b1, emb_ch, 1, h1);
-  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(h1, n_img, emb_ch, w2, b2, emb_ch, 1, se);
-  skinny_linear_kernel<<<(n_all + wpb - 1) / wpb, wpb * 32, 0, stream>>>(se, n_img, emb_ch, wall, ball, n_all, 0, out);
+  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(temb, uniq, model_ch, w1, b1, emb_ch, 1, h1);
+  skinny_linear_kernel<<<(emb_ch + wpb - 1) / wpb, wpb * 32, 0, stream>>>(h1, uniq, emb_ch, w2, b2, emb_ch, 1, se);
+  skinny_linear_kernel<<<(n_all + wpb - 1) / wpb, wpb * 32, 0, stream>>>(se, uniq, emb_ch, wall, ball, n_all, 0, out);
+  broadcast_rows_kernel<<<grid_for(static_cast<size_t>(n_img) * n_all, 256), 256, 0, stream>>>(out, n_img, n_all, rep);
   return cudaGetLastError();
 }
 

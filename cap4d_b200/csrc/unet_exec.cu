@@ -961,7 +961,7 @@ struct Unet {
         const float *w1 = te_w1, *b1 = te_b1, *w2 = te_w2, *b2 = te_b2, *wa = wall, *ba = ball;
         Op op;
         op.cls = CLS_OTHER;
-        op.launches = 4;
+        op.launches = 6;
         op.flops = 2.0 * n_img * (static_cast<double>(mc) * ech + static_cast<double>(ech) * ech +
                                   static_cast<double>(ech) * nall);
         op.bytes = 4.0 * (static_cast<double>(mc) * ech + static_cast<double>(ech) * ech + static_cast<double>(ech) * nall);
