@@ -78,30 +78,6 @@ __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __re
   }
 }
 
-// ---- fp32 NHWC -> bf16 NHWC nearest 2x (openaimodel.py:111-117) --------------------------------
-__global__ void upsample2x_kernel(const float* __restrict__ x, int n_img, int H, int W, int C, bf16* __restrict__ out) {
-  const int quads = C >> 2;
-  const size_t total = static_cast<size_t>(n_img) * H * W * quads;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int qd = static_cast<int>(i % quads);
-    const size_t pix = i / quads;
-    const int xx = static_cast<int>(pix % W);
-    const int yy = static_cast<int>((pix / W) % H);
-    const size_t n = pix / (static_cast<size_t>(W) * H);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    const uint2 u = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    const int W2 = 2 * W, H2 = 2 * H;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const size_t o = ((n * H2 + (2 * yy + dy)) * W2 + (2 * xx + dx)) * C + qd * 4;
-        *reinterpret_cast<uint2*>(out + o) = u;
-      }
-  }
-}
-
 // ---- fp32 NHWC -> bf16 parity planes for the stride-2 conv (openaimodel.py:150-153) ------------
 __global__ void parity_split_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
                                     bf16* __restrict__ out) {
@@ -338,12 +314,6 @@ cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int 
   const size_t total = static_cast<size_t>(B) * (V - R) * (per_img / 4);
   gather_views_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
                                                                 reinterpret_cast<float4*>(dst), B, V, R, per_img / 4);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_upsample2x_bf16(const float* x, int n_img, int H, int W, int C, bf16* out, cudaStream_t stream) {
-  const size_t total = static_cast<size_t>(n_img) * H * W * (C / 4);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, H, W, C, out);
   return cudaGetLastError();
 }
 

@@ -144,8 +144,6 @@ cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const flo
                               cudaStream_t stream);
 // dst image (b, g) = src image (b, R + g) for g < V - R: drops the R leading (reference) views of every group
 cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int R, size_t per_img, cudaStream_t stream);
-// fp32 NHWC -> bf16 NHWC, nearest 2x upsample
-cudaError_t launch_upsample2x_bf16(const float* x, int n_img, int H, int W, int C, bf16* out, cudaStream_t stream);
 // fp32 NHWC -> bf16 parity planes [4][n_img][H/2][W/2][C] (plane = (y&1)*2 + (x&1))
 cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, int C, bf16* out,
                                      cudaStream_t stream);

@@ -364,26 +364,6 @@ __device__ __forceinline__ float silu_f(float x) {
   return fmaf(hx, t, hx);
 }
 
-// erf GELU (torch.nn.functional.gelu default).  erf(z) = z * P(z^2) on |z| <= 3 (degree-8 minimax fit,
-// |error| <= 4e-5, erf saturates to 1 beyond; two orders of magnitude below the bf16 rounding of the
-// result): FMA-pipe only - the GEGLU epilogue is instruction-bound and MUFU runs at 1/8 the FMA rate.
-__device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 3.0f);
-  const float t = z * z;
-  float p = 4.918275920e-08f;
-  p = fmaf(p, t, -2.267730679e-06f);
-  p = fmaf(p, t, 4.614729187e-05f);
-  p = fmaf(p, t, -5.535572418e-04f);
-  p = fmaf(p, t, 4.437862430e-03f);
-  p = fmaf(p, t, -2.564961277e-02f);
-  p = fmaf(p, t, 1.118625030e-01f);
-  p = fmaf(p, t, -3.758186102e-01f);
-  p = fmaf(p, t, 1.128362894e+00f);
-  const float e = copysignf(fminf(z * p, 1.0f), x);  // erf(x / sqrt(2))
-  const float hx = 0.5f * x;
-  return fmaf(hx, e, hx);
-}
-
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 process two values per issue slot) ----
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -405,8 +385,10 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
-// y = a * gelu_erf(g) for two (a, g) pairs at once: the same polynomial as gelu_erf_f with the FMA chain
-// issued as FFMA2 (the GEGLU epilogue is bound by issue slots, not by the FMA pipe).
+// y = a * gelu(g) for two (a, g) pairs at once, erf GELU (torch.nn.functional.gelu default, attention.py:68-75).
+// erf(z) = z * P(z^2) on |z| <= 3 (degree-8 minimax fit, |error| <= 4e-5; erf saturates to 1 beyond; two orders of
+// magnitude below the bf16 rounding of the result): FMA pipe only - MUFU runs at 1/8 of its rate - and the
+// FMA chain is issued as FFMA2 because the GEGLU epilogue is bound by issue slots.
 __device__ __forceinline__ void geglu_pair(float& a0, float& a1, float g0, float g1) {
   const float z0 = fminf(fabsf(g0) * 0.70710678118654752f, 3.0f);
   const float z1 = fminf(fabsf(g1) * 0.70710678118654752f, 3.0f);
