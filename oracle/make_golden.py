@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import mmdm_oracle as O  # noqa: E402
 from oracle import ref_import as RI  # noqa: E402
+from oracle import vae_oracle as VO  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -94,6 +95,24 @@ def golden_sampler(name, n_ref, n_gen, S, R_max, cfg_scale, seed):
     print(name, tuple(z.shape), "absmax", float(z.abs().max()))
 
 
+def golden_vae(name, cfg, N, H, W, wseed, zseed):
+    """decode_first_stage of the reference: z / scale_factor -> AutoencoderKL.decode (ddpm.py:822-830)."""
+    vae = RI.build_reference_vae(cfg)
+    sd = VO.init_vae_state_dict(cfg, seed=wseed)
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.", "loss.")) for k in missing), missing
+    z = torch.randn(N, cfg["z_channels"], H, W, generator=torch.Generator().manual_seed(zseed)) * 0.8
+    feats = {}
+    hook = vae.decoder.mid.attn_1.register_forward_hook(lambda m, i, o: feats.__setitem__("attn", o.detach().clone()))
+    with torch.no_grad():
+        y = vae.decode(z / VO.SCALE_FACTOR)
+    hook.remove()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), N=N, H=H, W=W, wseed=wseed, zseed=zseed,
+                        cfg_keys=np.array(sorted(cfg.keys())), cfg_vals=np.array([str(cfg[k]) for k in sorted(cfg.keys())]),
+                        out=y.numpy(), mid_attn=feats["attn"].numpy())
+    print(name, tuple(y.shape), "std", float(y.std()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -102,3 +121,5 @@ if __name__ == "__main__":
     golden_schedule()
     golden_sampler("sampler_r1", n_ref=1, n_gen=6, S=4, R_max=4, cfg_scale=2.0, seed=124)
     golden_sampler("sampler_r2", n_ref=3, n_gen=4, S=5, R_max=2, cfg_scale=2.0, seed=7)
+    golden_vae("vae_tiny_h8", VO.TINY_VAE, N=2, H=8, W=8, wseed=0, zseed=1)
+    golden_vae("vae_tiny_h16x8", VO.TINY_VAE, N=1, H=16, W=8, wseed=3, zseed=4)

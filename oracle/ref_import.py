@@ -119,3 +119,16 @@ def build_reference_mmldm(cfg: dict):
         cond_stage_config="__is_unconditional__",
     )
     return model.eval()
+
+
+def build_reference_vae(cfg: dict):
+    """AutoencoderKL of configs/mmdm/cap4d_mmdm_final.yaml:117-139 (controlnet/ldm/models/autoencoder.py)."""
+    install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from controlnet.ldm.models.autoencoder import AutoencoderKL
+
+    dd = dict(double_z=True, z_channels=cfg["z_channels"], resolution=512, in_channels=3, out_ch=cfg["out_ch"],
+              ch=cfg["ch"], ch_mult=list(cfg["ch_mult"]), num_res_blocks=cfg["num_res_blocks"], attn_resolutions=[],
+              dropout=0.0)
+    return AutoencoderKL(ddconfig=dd, lossconfig={"target": "torch.nn.Identity"}, embed_dim=cfg["embed_dim"]).eval()

@@ -91,3 +91,34 @@ def test_param_census_production():
                         k in n for k in (".in_layers.0.", ".out_layers.0.", ".norm.", ".norm1.", ".norm3."))))
     # SURVEY.md note Z counts every all-zero parameter of a fresh model: zero_module()s + norm biases
     assert zero + norm_bias == 224_928_644
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE decode: oracle/vae_oracle.py against the reference AutoencoderKL fixtures
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vae_tiny_h8", "vae_tiny_h16x8"])
+def test_vae_oracle_matches_reference_fixture(name):
+    from oracle import vae_oracle as VO
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = VO.TINY_VAE
+    assert {k: str(cfg[k]) for k in sorted(cfg)} == dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
+    sd = VO.init_vae_state_dict(cfg, seed=int(g["wseed"]))
+    z = torch.randn(int(g["N"]), 4, int(g["H"]), int(g["W"]), generator=torch.Generator().manual_seed(int(g["zseed"]))) * 0.8
+    taps = {"decoder.mid.attn_1": None}
+    y = VO.vae_decode(sd, cfg, z, taps=taps)
+    ref = torch.from_numpy(g["out"])
+    assert y.shape == ref.shape == (int(g["N"]), 3, 8 * int(g["H"]), 8 * int(g["W"]))
+    assert O.max_rel_err(y, ref) < 2e-5
+    assert O.max_rel_err(taps["decoder.mid.attn_1"], torch.from_numpy(g["mid_attn"])) < 2e-5
+
+
+def test_vae_production_census():
+    from oracle import vae_oracle as VO
+
+    shapes = VO.vae_param_shapes(VO.PRODUCTION_VAE)
+    # decoder of the Stable-Diffusion KL-f8 autoencoder + post_quant_conv: 138 + 2 tensors, 49.49 M parameters
+    assert len(shapes) == 140
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 49_490_199
+    kinds = [k for k, *_ in VO.vae_decoder_topology(VO.PRODUCTION_VAE)]
+    assert kinds.count("res") == 14 and kinds.count("up") == 3 and kinds.count("attn") == 1
