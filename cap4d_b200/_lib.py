@@ -31,6 +31,18 @@ class UnetConfig(ctypes.Structure):
     ]
 
 
+class VaeConfig(ctypes.Structure):
+    _fields_ = [
+        ("ch", c_int),
+        ("n_levels", c_int),
+        ("ch_mult", c_int * MAX_LEVELS),
+        ("num_res_blocks", c_int),
+        ("z_channels", c_int),
+        ("embed_dim", c_int),
+        ("out_ch", c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/cap4d_b200.h declares
 SIGNATURES = {
     "cap4d_b200_unet_create": (c_int, [POINTER(UnetConfig), POINTER(c_void_p)]),
@@ -39,6 +51,16 @@ SIGNATURES = {
     "cap4d_b200_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "cap4d_b200_unet_finalize": (c_int, [c_void_p]),
     "cap4d_b200_unet_set_ref_views": (c_int, [c_void_p, c_int]),
+    "cap4d_b200_vae_create": (c_int, [POINTER(VaeConfig), POINTER(c_void_p)]),
+    "cap4d_b200_vae_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    "cap4d_b200_vae_num_params": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_vae_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
+    "cap4d_b200_vae_finalize": (c_int, [c_void_p]),
+    "cap4d_b200_vae_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "cap4d_b200_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p,
+                                      c_size_t, c_void_p]),
+    "cap4d_b200_vae_num_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_vae_destroy": (c_int, [c_void_p]),
     "cap4d_b200_unet_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "cap4d_b200_unet_forward": (
         c_int,

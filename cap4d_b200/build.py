@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcap4d_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu"]
-HEADERS = ["ptx.cuh", "kernels.h", os.path.join("..", "..", "include", "cap4d_b200.h")]
+SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu", "vae_exec.cu"]
+HEADERS = ["ptx.cuh", "kernels.h", "exec_common.h", os.path.join("..", "..", "include", "cap4d_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -187,6 +187,102 @@ __global__ void skinny_linear_kernel(const float* __restrict__ in, const int* __
   }
 }
 
+// ---- VAE decode helpers (controlnet/ldm/models/autoencoder.py:87-91, diffusionmodules/model.py) -------
+// Input stage: z / scale_factor (ddpm.py:829) -> post_quant_conv (1x1, 4 -> 4) -> im2col rows for conv_in
+// (3x3, pad 1): out[n*h*w + y*w + x][tap*zc + c], K padded with zeros to kpad.  Padding taps are zero AFTER
+// post_quant_conv (conv_in pads its own input).
+__global__ void vae_input_pack_kernel(const float* __restrict__ z, int n_img, int zc, int H, int W,
+                                      const float* __restrict__ wpq, const float* __restrict__ bpq, float inv_scale,
+                                      int kpad, bf16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n_img) * H * W * 9;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % 9);
+    const size_t pix = i / 9;
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    bf16* dst = out + pix * kpad + tap * zc;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+      for (int c = 0; c < zc; ++c) dst[c] = __float2bfloat16(0.f);
+    } else {
+      for (int co = 0; co < zc; ++co) {
+        float v = bpq[co];
+        for (int ci = 0; ci < zc; ++ci)
+          v = fmaf(wpq[co * zc + ci], z[((n * zc + ci) * H + yy) * W + xx] * inv_scale, v);
+        dst[co] = __float2bfloat16(v);
+      }
+    }
+    if (tap == 8)
+      for (int k = 9 * zc; k < kpad; ++k) out[pix * kpad + k] = __float2bfloat16(0.f);
+  }
+}
+
+// h fp32 NHWC [n*H*W][ldh] (first cout columns) -> images fp32 NCHW [n][cout][H][W]
+__global__ void vae_output_kernel(const float* __restrict__ h, int ldh, int n_img, int cout, int H, int W,
+                                  float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n_img) * cout * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t sp = i % (static_cast<size_t>(H) * W);
+    const int c = static_cast<int>((i / (static_cast<size_t>(H) * W)) % cout);
+    const size_t n = i / (static_cast<size_t>(H) * W * cout);
+    out[i] = h[(n * H * W + sp) * ldh + c];
+  }
+}
+
+// softmax over the rows of fp32 scores [rows][L] (times scale) -> bf16 probabilities; one block per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int L, float scale,
+                                                           bf16* __restrict__ p) {
+  __shared__ float red[8];
+  const float* row = s + static_cast<size_t>(blockIdx.x) * L;
+  bf16* prow = p + static_cast<size_t>(blockIdx.x) * L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x * 4; i < L; i += blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < L; i += blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+    sum += expf((v.x - m) * scale) + expf((v.y - m) * scale) + expf((v.z - m) * scale) + expf((v.w - m) * scale);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x * 4; i < L; i += blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+    const uint2 u = make_uint2(pack_bf16x2(expf((v.x - m) * scale) * inv, expf((v.y - m) * scale) * inv),
+                               pack_bf16x2(expf((v.z - m) * scale) * inv, expf((v.w - m) * scale) * inv));
+    *reinterpret_cast<uint2*>(prow + i) = u;
+  }
+}
+
+// dst[c][r] = src[r][c] for r < rows, c < cols (src row stride ld): 32x32 tiles through shared memory
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ src, int ld, int rows, int cols, bf16* __restrict__ dst) {
+  __shared__ bf16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[static_cast<size_t>(r) * ld + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[static_cast<size_t>(c) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
 // ---- weight repacks ---------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW,
                                         bf16* __restrict__ out, int ldk, int k_offset) {
@@ -391,6 +487,39 @@ cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long 
   const size_t total = static_cast<size_t>(n_groups) * (V - R) * (chw / 4);
   cfg_ddim_kernel<<<grid_for(total, 256), 256, 0, stream>>>(latents, eps, gen_idx, n_groups, V, R, chw, cfg, x_coef,
                                                             e_coef);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vae_input_pack(const float* z, int n_img, int zc, int H, int W, const float* wpq, const float* bpq,
+                                  float inv_scale, int kpad, bf16* out, cudaStream_t stream) {
+  if (9 * zc > kpad) {
+    set_error("vae_input_pack: 9 * z_channels must fit the padded K");
+    return cudaErrorInvalidValue;
+  }
+  const size_t total = static_cast<size_t>(n_img) * H * W * 9;
+  vae_input_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(z, n_img, zc, H, W, wpq, bpq, inv_scale, kpad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vae_output(const float* h, int ldh, int n_img, int cout, int H, int W, float* out,
+                              cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_img) * cout * H * W;
+  vae_output_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, n_img, cout, H, W, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_rows(const float* s, int rows, int L, float scale, bf16* p, cudaStream_t stream) {
+  if (L % 4 != 0) {
+    set_error("softmax_rows: L must be a multiple of 4");
+    return cudaErrorInvalidValue;
+  }
+  softmax_rows_kernel<<<rows, 256, 0, stream>>>(s, L, scale, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_bf16(const bf16* src, int ld, int rows, int cols, bf16* dst, cudaStream_t stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(src, ld, rows, cols, dst);
   return cudaGetLastError();
 }
 

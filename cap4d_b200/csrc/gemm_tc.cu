@@ -160,14 +160,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_tile = tile / p.tiles_n;
         const int n_tile = tile - m_tile * p.tiles_n;
         // per-tile coordinates of the (up to two) 128-row sub-tiles; nothing in the k loop divides
-        int row0[2], n0[2], y0[2];
+        int row0[2], n0[2], y0[2], x0[2];
         for (int sub = 0; sub < 2; ++sub) {
           row0[sub] = (m_tile * p.msub + sub) * BM;  // first output row (pixel) of the sub-tile
-          n0[sub] = y0[sub] = 0;
+          n0[sub] = y0[sub] = x0[sub] = 0;
           if (p.a_conv) {
             const int hw = p.H * p.W;
             n0[sub] = row0[sub] / hw;
             y0[sub] = (row0[sub] - n0[sub] * hw) / p.W;
+            x0[sub] = row0[sub] - n0[sub] * hw - y0[sub] * p.W;  // != 0 only when an image row is wider than a tile
           }
         }
         const int b_row = n_tile * p.BN;
@@ -179,8 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kb < p.seg0_kb) {
             if (p.a_conv) {
               const int dx = p.tap_dx[tap], dy = p.tap_dy[tap], dn = p.tap_dn[tap];
-              tma_load_4d(dstA, &tmA, &tail->full[stage], c0, dx, y0[0] + dy, n0[0] + dn);
-              if (p.msub == 2) tma_load_4d(dstA + A_SUB_BYTES, &tmA, &tail->full[stage], c0, dx, y0[1] + dy, n0[1] + dn);
+              tma_load_4d(dstA, &tmA, &tail->full[stage], c0, x0[0] + dx, y0[0] + dy, n0[0] + dn);
+              if (p.msub == 2)
+                tma_load_4d(dstA + A_SUB_BYTES, &tmA, &tail->full[stage], c0, x0[1] + dx, y0[1] + dy, n0[1] + dn);
               c0 += BK;
               if (c0 == p.cin_kb * BK) {
                 c0 = 0;
@@ -397,11 +399,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m_tile = pt / p.tiles_n;
         const int n_tile = pt - m_tile * p.tiles_n;
         const int row0 = m_tile * 2 * BM + static_cast<int>(rank) * BM;  // first output row of this CTA's half
-        int n0 = 0, y0 = 0;
+        int n0 = 0, y0 = 0, x0 = 0;
         if (p.a_conv) {
           const int hw = p.H * p.W;
           n0 = row0 / hw;
           y0 = (row0 - n0 * hw) / p.W;
+          x0 = row0 - n0 * hw - y0 * p.W;
         }
         const int b_row = n_tile * p.BN + static_cast<int>(rank) * b_half;
         int tap = 0, c0 = 0;
@@ -411,7 +414,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* dstA = sA + stage * a_stage_bytes;
           if (kb < p.seg0_kb) {
             if (p.a_conv) {
-              tma_load_4d_2sm(dstA, &tmA, &tail->full[stage], c0, p.tap_dx[tap], y0 + p.tap_dy[tap], n0 + p.tap_dn[tap]);
+              tma_load_4d_2sm(dstA, &tmA, &tail->full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
+                              n0 + p.tap_dn[tap]);
               c0 += BK;
               if (c0 == p.cin_kb * BK) {
                 c0 = 0;
@@ -698,7 +702,7 @@ bool apply_cfg(GemmPlan* plan, const TileCfg& cfg, const bf16* Wt, int N, int Kt
                            : std::min(p.tiles_m * p.tiles_n, sm_count());
   // weights: [N][Ktot] row-major
   uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};
-  uint64_t strides[2] = {1, static_cast<uint64_t>(Ktot)};
+  uint64_t strides[2] = {1, static_cast<uint64_t>(plan->ldw > 0 ? plan->ldw : Ktot)};
   uint32_t box[2] = {BK, static_cast<uint32_t>(cfg.two_cta ? bn / 2 : bn)};
   return make_tmap_bf16(&plan->tmB, Wt, 2, dims, strides, box);
 }
@@ -729,9 +733,9 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
   return apply_cfg(plan, cfg, Wt, N, Ktot);
 }
 
-bool make_plain_a_map(CUtensorMap* map, const bf16* A, int M, int K) {
+bool make_plain_a_map(CUtensorMap* map, const bf16* A, int M, int K, int lda = 0) {
   uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-  uint64_t strides[2] = {1, static_cast<uint64_t>(K)};
+  uint64_t strides[2] = {1, static_cast<uint64_t>(lda > 0 ? lda : K)};
   uint32_t box[2] = {BK, BM};
   return make_tmap_bf16(map, A, 2, dims, strides, box);
 }
@@ -836,9 +840,14 @@ bool autotune(GemmPlan* plan, const bf16* Wt, int N, int Ktot) {
 
 bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2, int K2, const bf16* Wt, int N,
                     int out_mode, void* out, int ldo, const float* bias, const float* rowbias, int rowbias_div,
-                    int rowbias_ld, const float* residual, int ldr) {
+                    int rowbias_ld, const float* residual, int ldr, int lda, int ldw) {
   memset(plan, 0, sizeof(*plan));
   GemmParams& p = plan->p;
+  if ((lda % 8) != 0 || (ldw % 8) != 0 || (ldw > 0 && A2 != nullptr)) {
+    set_error("gemm: lda / ldw must be multiples of 8 (and ldw excludes a second A segment)");
+    return false;
+  }
+  plan->ldw = ldw;
   if (K % BK != 0 || (A2 != nullptr && K2 % BK != 0)) {
     set_error("gemm: K must be a multiple of 64");
     return false;
@@ -848,7 +857,7 @@ bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2,
   p.seg0_kb = K / BK;
   p.cin_kb = 1;
   p.n_taps = 1;
-  if (!make_plain_a_map(&plan->tmA, A, M, K)) return false;
+  if (!make_plain_a_map(&plan->tmA, A, M, K, lda)) return false;
   if (A2 != nullptr) {
     if (!make_plain_a_map(&plan->tmA2, A2, M, K2)) return false;
   } else {
@@ -868,8 +877,12 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
   GemmParams& p = plan->p;
   const int H = g.H, W = g.W;
   auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-  if (!is_pow2(W) || !is_pow2(H) || W > BM) {
-    set_error("conv: output H and W must be powers of two with W <= 128");
+  if (!is_pow2(W) || !is_pow2(H)) {
+    set_error("conv: output H and W must be powers of two");
+    return false;
+  }
+  if (W > BM && g.stride != 1) {
+    set_error("conv: stride 2 needs W <= 128");
     return false;
   }
   if (Cin % BK != 0 || (A2 != nullptr && K2 % BK != 0)) {
@@ -889,8 +902,11 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
   p.seg0_kb = ntaps * p.cin_kb;
   p.W = W;
   p.H = H;
-  p.box_h = std::min(H, BM / W);
-  p.box_n = BM / (W * p.box_h);
+  // an M sub-tile is 128 consecutive pixels: box_n images x box_h rows x box_w pixels (a piece of ONE row
+  // when the image is wider than 128)
+  const int box_w = std::min(W, BM);
+  p.box_h = std::max(1, std::min(H, BM / W));
+  p.box_n = BM / (box_w * p.box_h);
   p.n_taps = ntaps;
   int planes = 1;
   if (up) {
@@ -924,7 +940,7 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
                         static_cast<uint64_t>(g.n_img) * planes};
     uint64_t strides[4] = {1, static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cin) * W,
                            static_cast<uint64_t>(Cin) * W * H};
-    uint32_t box[4] = {BK, static_cast<uint32_t>(W), static_cast<uint32_t>(p.box_h),
+    uint32_t box[4] = {BK, static_cast<uint32_t>(box_w), static_cast<uint32_t>(p.box_h),
                        static_cast<uint32_t>(p.box_n)};
     if (!make_tmap_bf16(&plan->tmA, A, 4, dims, strides, box)) return false;
   }

@@ -62,6 +62,7 @@ struct GemmPlan {
   int grid;
   size_t smem_bytes;
   double flops;  // 2*M*N*K, for reporting
+  int ldw;       // row stride of the weight matrix in elements (0: dense, = K)
 };
 
 struct ConvGeom {
@@ -78,7 +79,9 @@ struct ConvGeom {
 // Returns false (and sets the error text) on invalid geometry.
 bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2, int K2, const bf16* Wt, int N,
                     int out_mode, void* out, int ldo, const float* bias, const float* rowbias, int rowbias_div,
-                    int rowbias_ld, const float* residual, int ldr);
+                    int rowbias_ld, const float* residual, int ldr, int lda = 0, int ldw = 0);
+// lda / ldw: row strides of A and Wt in elements when they are column slices of wider matrices (0: dense);
+// multiples of 8 (TMA needs 16 B strides).
 
 // Implicit-GEMM 3x3 convolution, pad 1: A NHWC bf16 [n_img][H_in][W_in][Cin]
 // (stride 2: parity planes, see ConvGeom).  Optional A2 [M][K2] plain segment.
@@ -167,6 +170,18 @@ cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, i
 cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream);
 // fp32 -> bf16 copy
 cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t stream);
+
+// ---- VAE decode helpers (elementwise.cu) ----
+// z NCHW fp32 -> (z / scale) -> post_quant_conv -> im2col rows [n*H*W][kpad] bf16 for conv_in (3x3, pad 1)
+cudaError_t launch_vae_input_pack(const float* z, int n_img, int zc, int H, int W, const float* wpq, const float* bpq,
+                                  float inv_scale, int kpad, bf16* out, cudaStream_t stream);
+// fp32 NHWC [n*H*W][ldh] -> fp32 NCHW [n][cout][H][W]
+cudaError_t launch_vae_output(const float* h, int ldh, int n_img, int cout, int H, int W, float* out,
+                              cudaStream_t stream);
+// softmax(scale * s) over rows of fp32 [rows][L] -> bf16
+cudaError_t launch_softmax_rows(const float* s, int rows, int L, float scale, bf16* p, cudaStream_t stream);
+// dst[cols][rows] = src[rows][cols] (src row stride ld)
+cudaError_t launch_transpose_bf16(const bf16* src, int ld, int rows, int cols, bf16* dst, cudaStream_t stream);
 cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, int ldk, int k_offset, int row_offset,
                                cudaStream_t stream);                     // out[row_offset + r][k_offset + c]
 

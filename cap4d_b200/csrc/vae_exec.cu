@@ -1,0 +1,705 @@
+// VAE decoder executor (the step on the output side of the sampler).
+//
+// Mirrors decode_first_stage (controlnet/ldm/models/diffusion/ddpm.py:822-830: z / scale_factor) ->
+// AutoencoderKL.decode (controlnet/ldm/models/autoencoder.py:87-91: post_quant_conv, decoder) -> Decoder.forward
+// (controlnet/ldm/modules/diffusionmodules/model.py:606-640) with ResnetBlock (:125-146, temb = None),
+// AttnBlock (:176-203) and Upsample (:71-76).  Same kernel family as the U-Net: GroupNorm+SiLU ->
+// bf16 operand, implicit-GEMM conv3x3 with the 1x1 nin_shortcut appended along K, nearest-2x + conv3x3
+// folded into four phase convs.  The single mid-block attention is one head over all C channels
+// (C = 512, 4096 tokens): scores, softmax and P.V are three launches per image through a materialised
+// fp32 score matrix (64 MB) - 3 % of the decoder's FLOPs, not worth a second flash kernel.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cap4d_b200.h"
+#include "exec_common.h"
+#include "kernels.h"
+
+namespace cap4d {
+
+namespace {
+
+struct VRes {
+  std::string prefix;
+  int cin = 0, cout = 0;
+  bool skip = false;
+  float *gn1_g = nullptr, *gn1_b = nullptr, *gn2_g = nullptr, *gn2_b = nullptr;
+  bf16 *w1 = nullptr, *w2 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr;
+};
+struct VAttn {
+  std::string prefix;
+  int C = 0;
+  float *gn_g = nullptr, *gn_b = nullptr;
+  bf16 *wqkv = nullptr, *wo = nullptr;
+  float *bqkv = nullptr, *bo = nullptr;
+};
+struct VConv {
+  std::string prefix;
+  int cin = 0, cout = 0;
+  bf16* w = nullptr;
+  float* b = nullptr;
+};
+enum VKind { V_RES, V_ATTN, V_UP };
+struct VLayer {
+  VKind kind;
+  int idx;
+};
+
+struct Vae {
+  cap4d_b200_vae_config cfg;
+  std::vector<VRes> res;
+  std::vector<VAttn> attn;
+  std::vector<VConv> up;
+  std::vector<VLayer> layers;
+  int c_in = 0, c_last = 0, kpad_in = 64;
+  std::map<std::string, RawTensor> raw;
+  std::vector<void*> owned;
+  bool finalized = false;
+  bf16* w_in = nullptr;
+  float *b_in = nullptr, *w_pq = nullptr, *b_pq = nullptr, *out_gn_g = nullptr, *out_gn_b = nullptr, *b_out = nullptr;
+  bf16* w_out = nullptr;
+  // plan
+  std::vector<Op> ops;
+  const float* io_z = nullptr;
+  float* io_out = nullptr;
+  float io_inv_scale = 1.f;
+  int pN = 0, pH = 0, pW = 0;
+  void* p_ws = nullptr;
+  size_t p_ws_bytes = 0;
+
+  ~Vae() {
+    for (void* p : owned) cudaFree(p);
+    for (auto& kv : raw)
+      if (kv.second.d) cudaFree(kv.second.d);
+  }
+
+  // ------------------------------------------------------------------ topology (model.py:546-604)
+  bool build_topology() {
+    if (cfg.n_levels < 1 || cfg.n_levels > 8 || cfg.ch % 32 != 0 || cfg.z_channels < 1 || 9 * cfg.z_channels > kpad_in ||
+        cfg.out_ch < 1 || cfg.out_ch > 32 || cfg.num_res_blocks < 0) {
+      set_error("vae: unsupported configuration (ch must be a multiple of 32, 9*z_channels <= 64, out_ch <= 32)");
+      return false;
+    }
+    int block_in = cfg.ch * cfg.ch_mult[cfg.n_levels - 1];
+    c_in = block_in;
+    auto add_res = [&](const std::string& p, int cin, int cout) {
+      VRes r;
+      r.prefix = p;
+      r.cin = cin;
+      r.cout = cout;
+      r.skip = cin != cout;
+      res.push_back(r);
+      layers.push_back({V_RES, static_cast<int>(res.size()) - 1});
+    };
+    add_res("decoder.mid.block_1.", block_in, block_in);
+    {
+      VAttn a;
+      a.prefix = "decoder.mid.attn_1.";
+      a.C = block_in;
+      attn.push_back(a);
+      layers.push_back({V_ATTN, 0});
+    }
+    add_res("decoder.mid.block_2.", block_in, block_in);
+    for (int lvl = cfg.n_levels - 1; lvl >= 0; --lvl) {
+      const int block_out = cfg.ch * cfg.ch_mult[lvl];
+      if (block_out % 64 != 0 && block_out % 32 != 0) {
+        set_error("vae: channel counts must be multiples of 32");
+        return false;
+      }
+      for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+        add_res("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(i) + ".", block_in, block_out);
+        block_in = block_out;
+      }
+      if (lvl != 0) {
+        VConv u;
+        u.prefix = "decoder.up." + std::to_string(lvl) + ".upsample.conv.";
+        u.cin = u.cout = block_in;
+        up.push_back(u);
+        layers.push_back({V_UP, static_cast<int>(up.size()) - 1});
+      }
+    }
+    c_last = block_in;
+    for (const VRes& r : res)
+      if (r.cin % 64 != 0 || r.cout % 32 != 0) {
+        set_error("vae: ResnetBlock channels must be multiples of 64 (in) / 32 (out) for the conv kernel");
+        return false;
+      }
+    return true;
+  }
+
+  std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params() const {
+    std::vector<std::pair<std::string, std::vector<int64_t>>> v;
+    auto add = [&](const std::string& n, std::vector<int64_t> s) { v.emplace_back(n, std::move(s)); };
+    const int zc = cfg.z_channels;
+    add("post_quant_conv.weight", {zc, cfg.embed_dim, 1, 1});
+    add("post_quant_conv.bias", {zc});
+    add("decoder.conv_in.weight", {c_in, zc, 3, 3});
+    add("decoder.conv_in.bias", {c_in});
+    for (const VRes& r : res) {
+      add(r.prefix + "norm1.weight", {r.cin});
+      add(r.prefix + "norm1.bias", {r.cin});
+      add(r.prefix + "conv1.weight", {r.cout, r.cin, 3, 3});
+      add(r.prefix + "conv1.bias", {r.cout});
+      add(r.prefix + "norm2.weight", {r.cout});
+      add(r.prefix + "norm2.bias", {r.cout});
+      add(r.prefix + "conv2.weight", {r.cout, r.cout, 3, 3});
+      add(r.prefix + "conv2.bias", {r.cout});
+      if (r.skip) {
+        add(r.prefix + "nin_shortcut.weight", {r.cout, r.cin, 1, 1});
+        add(r.prefix + "nin_shortcut.bias", {r.cout});
+      }
+    }
+    for (const VAttn& a : attn) {
+      add(a.prefix + "norm.weight", {a.C});
+      add(a.prefix + "norm.bias", {a.C});
+      for (const char* n : {"q", "k", "v", "proj_out"}) {
+        add(a.prefix + n + ".weight", {a.C, a.C, 1, 1});
+        add(a.prefix + n + ".bias", {a.C});
+      }
+    }
+    for (const VConv& u : up) {
+      add(u.prefix + "weight", {u.cout, u.cin, 3, 3});
+      add(u.prefix + "bias", {u.cout});
+    }
+    add("decoder.norm_out.weight", {c_last});
+    add("decoder.norm_out.bias", {c_last});
+    add("decoder.conv_out.weight", {cfg.out_ch, c_last, 3, 3});
+    add("decoder.conv_out.bias", {cfg.out_ch});
+    return v;
+  }
+
+  // ------------------------------------------------------------------ weights
+  template <typename T>
+  T* dev_alloc(size_t n, bool zero = false) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 16));
+    owned.push_back(p);
+    return static_cast<T*>(p);
+  }
+  bool get(const std::string& name, size_t numel, const RawTensor** out) {
+    auto it = raw.find(name);
+    if (it == raw.end()) {
+      set_error("missing weight: " + name);
+      return false;
+    }
+    if (it->second.numel != numel) {
+      set_error("weight " + name + ": expected " + std::to_string(numel) + " elements, got " +
+                std::to_string(it->second.numel));
+      return false;
+    }
+    *out = &it->second;
+    return true;
+  }
+  bool fp(const std::string& name, size_t numel, float** out) {
+    const RawTensor* t;
+    if (!get(name, numel, &t)) return false;
+    *out = t->d;
+    return true;
+  }
+  bool pack_conv(const std::string& name, int cout, int cin, bf16* dst, int ldk) {
+    const RawTensor* t;
+    if (!get(name, static_cast<size_t>(cout) * cin * 9, &t)) return false;
+    CUDA_OK(launch_pack_conv_weight(t->d, cout, cin, 3, 3, dst, ldk, 0, 0));
+    return true;
+  }
+
+  bool finalize() {
+    if (finalized) return true;
+    for (const auto& kv : expected_params()) {
+      size_t n = 1;
+      for (int64_t d : kv.second) n *= static_cast<size_t>(d);
+      const RawTensor* t;
+      if (!get(kv.first, n, &t)) return false;
+    }
+    const RawTensor* t;
+    const int zc = cfg.z_channels;
+    if (cfg.embed_dim != zc) {
+      set_error("vae: embed_dim != z_channels is not implemented");
+      return false;
+    }
+    if (!fp("post_quant_conv.weight", static_cast<size_t>(zc) * zc, &w_pq) || !fp("post_quant_conv.bias", zc, &b_pq) ||
+        !fp("decoder.conv_in.bias", c_in, &b_in))
+      return false;
+    // conv_in over im2col rows [tap*zc + c], K padded to 64 (vae_input_pack_kernel)
+    w_in = dev_alloc<bf16>(static_cast<size_t>(c_in) * kpad_in, true);
+    if (!w_in || !pack_conv("decoder.conv_in.weight", c_in, zc, w_in, kpad_in)) return false;
+    for (VRes& r : res) {
+      const std::string& p = r.prefix;
+      if (!fp(p + "norm1.weight", r.cin, &r.gn1_g) || !fp(p + "norm1.bias", r.cin, &r.gn1_b) ||
+          !fp(p + "norm2.weight", r.cout, &r.gn2_g) || !fp(p + "norm2.bias", r.cout, &r.gn2_b) ||
+          !fp(p + "conv1.bias", r.cout, &r.b1))
+        return false;
+      r.w1 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * 9 * r.cin);
+      const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
+      r.w2 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * k2);
+      r.b2 = dev_alloc<float>(r.cout);
+      if (!r.w1 || !r.w2 || !r.b2) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      if (!pack_conv(p + "conv1.weight", r.cout, r.cin, r.w1, 9 * r.cin)) return false;
+      if (!pack_conv(p + "conv2.weight", r.cout, r.cout, r.w2, k2)) return false;
+      float *bo, *bs = nullptr;
+      if (!fp(p + "conv2.bias", r.cout, &bo)) return false;
+      if (r.skip) {  // nin_shortcut (model.py:113-123) appended along K of conv2
+        if (!get(p + "nin_shortcut.weight", static_cast<size_t>(r.cout) * r.cin, &t)) return false;
+        CUDA_OK(launch_pack_matrix(t->d, r.cout, r.cin, r.w2, k2, 9 * r.cout, 0, 0));
+        if (!fp(p + "nin_shortcut.bias", r.cout, &bs)) return false;
+      }
+      vec_add_kernel<<<(r.cout + 255) / 256, 256>>>(bo, bs, r.b2, r.cout);
+    }
+    for (VAttn& a : attn) {
+      const int C = a.C;
+      if (!fp(a.prefix + "norm.weight", C, &a.gn_g) || !fp(a.prefix + "norm.bias", C, &a.gn_b) ||
+          !fp(a.prefix + "proj_out.bias", C, &a.bo))
+        return false;
+      a.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
+      a.bqkv = dev_alloc<float>(static_cast<size_t>(3) * C);
+      a.wo = dev_alloc<bf16>(static_cast<size_t>(C) * C);
+      if (!a.wqkv || !a.bqkv || !a.wo) {
+        set_error("cudaMalloc failed");
+        return false;
+      }
+      const char* names[3] = {"q", "k", "v"};
+      for (int i = 0; i < 3; ++i) {  // 1x1 convs == linears: rows [i*C, (i+1)*C) of the fused [3C][C] matrix
+        if (!get(a.prefix + names[i] + ".weight", static_cast<size_t>(C) * C, &t)) return false;
+        CUDA_OK(launch_pack_matrix(t->d, C, C, a.wqkv, C, 0, i * C, 0));
+        if (!get(a.prefix + names[i] + ".bias", C, &t)) return false;
+        CUDA_OK(cudaMemcpy(a.bqkv + static_cast<size_t>(i) * C, t->d, C * sizeof(float), cudaMemcpyDeviceToDevice));
+      }
+      if (!get(a.prefix + "proj_out.weight", static_cast<size_t>(C) * C, &t)) return false;
+      CUDA_OK(launch_pack_matrix(t->d, C, C, a.wo, C, 0, 0, 0));
+    }
+    for (VConv& u : up) {
+      u.w = dev_alloc<bf16>(static_cast<size_t>(16) * u.cout * u.cin);  // 4 phases x [cout][4*cin]
+      if (!u.w || !get(u.prefix + "weight", static_cast<size_t>(u.cout) * u.cin * 9, &t)) return false;
+      CUDA_OK(launch_pack_upconv_weight(t->d, u.cout, u.cin, u.w, 0));
+      if (!fp(u.prefix + "bias", u.cout, &u.b)) return false;
+    }
+    if (!fp("decoder.norm_out.weight", c_last, &out_gn_g) || !fp("decoder.norm_out.bias", c_last, &out_gn_b)) return false;
+    w_out = dev_alloc<bf16>(static_cast<size_t>(32) * 9 * c_last, true);  // N padded to 32
+    b_out = dev_alloc<float>(32, true);
+    if (!w_out || !b_out || !pack_conv("decoder.conv_out.weight", cfg.out_ch, c_last, w_out, 9 * c_last)) return false;
+    if (!get("decoder.conv_out.bias", cfg.out_ch, &t)) return false;
+    CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_ch * sizeof(float), cudaMemcpyDeviceToDevice));
+    CUDA_OK(cudaDeviceSynchronize());
+    finalized = true;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ planning
+  struct Ctx {
+    Arena arena;
+    bool dry = true;
+    uint8_t* base = nullptr;
+    int n_img = 0;
+    float* gn_partial = nullptr;
+    std::vector<Op>* ops = nullptr;
+    template <typename T>
+    T* ptr(const Buf& b) const {
+      return reinterpret_cast<T*>(base + b.off);
+    }
+    Buf alloc(size_t M, int C, size_t elem) {
+      Buf b;
+      b.M = static_cast<int>(M);
+      b.C = C;
+      b.bytes = M * C * elem;
+      b.off = arena.alloc(b.bytes);
+      b.valid = true;
+      return b;
+    }
+    void release(Buf& b) {
+      if (b.valid) arena.release(b.off, b.bytes);
+      b.valid = false;
+    }
+  };
+
+  void push(Ctx& c, int cls, double flops, double bytes, std::function<cudaError_t(cudaStream_t)> fn) {
+    Op op;
+    op.cls = cls;
+    op.launches = 1;
+    op.flops = flops;
+    op.bytes = bytes;
+    op.run = std::move(fn);
+    c.ops->push_back(op);
+  }
+
+  bool op_gn(Ctx& c, const Buf& x, int hw, const float* g, const float* b, int silu, const Buf& out, const Buf* raw_out) {
+    if (c.dry) return true;
+    const float* px = c.ptr<float>(x);
+    bf16* po = c.ptr<bf16>(out);
+    bf16* pr = raw_out ? c.ptr<bf16>(*raw_out) : nullptr;
+    float* partial = c.gn_partial;
+    const int n_img = c.n_img, C = x.C;
+    push(c, CLS_GN, 0, static_cast<double>(x.M) * C * (4 + 2 + (raw_out ? 2 : 0)), [=](cudaStream_t s) {
+      return launch_groupnorm(px, C, nullptr, 0, n_img, hw, g, b, 1e-6f, silu, po, pr, partial, s);  // model.py:46-47
+    });
+    return true;
+  }
+
+  bool conv_op(Ctx& c, const bf16* A, int H, int W, int cin, const bf16* A2, int K2, const bf16* Wt, int cout, float* out,
+               const float* bias, const float* residual) {
+    GemmPlan p;
+    ConvGeom g{c.n_img, H, W, 9, 1};
+    if (!make_conv_plan(&p, A, g, cin, A2, K2, Wt, cout, OUT_F32, out, cout, bias, nullptr, 1, 0, residual, cout))
+      return false;
+    GemmPlan copy = p;
+    push(c, CLS_CONV, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+    return true;
+  }
+
+  // ResnetBlock.forward with temb = None (model.py:125-146)
+  bool plan_res(Ctx& c, const VRes& r, const Buf& x, int H, int W, Buf* out) {
+    const size_t M = x.M;
+    const int hw = H * W;
+    Buf a1 = c.alloc(M, r.cin, 2), xb;
+    if (r.skip) xb = c.alloc(M, r.cin, 2);
+    if (!op_gn(c, x, hw, r.gn1_g, r.gn1_b, 1, a1, r.skip ? &xb : nullptr)) return false;
+    Buf h = c.alloc(M, r.cout, 4);
+    if (!c.dry && !conv_op(c, c.ptr<bf16>(a1), H, W, r.cin, nullptr, 0, r.w1, r.cout, c.ptr<float>(h), r.b1, nullptr))
+      return false;
+    c.release(a1);
+    Buf a2 = c.alloc(M, r.cout, 2);
+    if (!op_gn(c, h, hw, r.gn2_g, r.gn2_b, 1, a2, nullptr)) return false;
+    c.release(h);
+    *out = c.alloc(M, r.cout, 4);
+    if (!c.dry && !conv_op(c, c.ptr<bf16>(a2), H, W, r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? r.cin : 0, r.w2,
+                           r.cout, c.ptr<float>(*out), r.b2, r.skip ? nullptr : c.ptr<float>(x)))
+      return false;
+    c.release(a2);
+    c.release(xb);
+    return true;
+  }
+
+  // AttnBlock.forward (model.py:176-203): one head over all C channels
+  bool plan_attn(Ctx& c, const VAttn& w, const Buf& x, int H, int W, Buf* out) {
+    const int C = w.C, L = H * W;
+    const size_t M = x.M;
+    Buf a = c.alloc(M, C, 2);
+    if (!op_gn(c, x, L, w.gn_g, w.gn_b, 0, a, nullptr)) return false;
+    Buf qkv = c.alloc(M, 3 * C, 2);
+    Buf o = c.alloc(M, C, 2);
+    Buf sc = c.alloc(L, L, 4), pr = c.alloc(L, L, 2), vt = c.alloc(C, L, 2);
+    *out = c.alloc(M, C, 4);
+    if (!c.dry) {
+      GemmPlan p;
+      if (!make_gemm_plan(&p, c.ptr<bf16>(a), static_cast<int>(M), C, nullptr, 0, w.wqkv, 3 * C, OUT_BF16, c.ptr<bf16>(qkv),
+                          3 * C, w.bqkv, nullptr, 1, 0, nullptr, 0))
+        return false;
+      {
+        GemmPlan copy = p;
+        push(c, CLS_LINEAR, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+      }
+      const float scale = 1.0f / sqrtf(static_cast<float>(C));
+      for (int n = 0; n < c.n_img; ++n) {
+        const bf16* q = c.ptr<bf16>(qkv) + static_cast<size_t>(n) * L * 3 * C;
+        float* ps = c.ptr<float>(sc);
+        bf16* pp = c.ptr<bf16>(pr);
+        bf16* pvt = c.ptr<bf16>(vt);
+        // scores[i][j] = q_i . k_j : A = Q (row stride 3C), "weights" = K (row stride 3C)
+        if (!make_gemm_plan(&p, q, L, C, nullptr, 0, q + C, L, OUT_F32, ps, L, nullptr, nullptr, 1, 0, nullptr, 0, 3 * C,
+                            3 * C))
+          return false;
+        {
+          GemmPlan copy = p;
+          push(c, CLS_ATTN, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+        }
+        push(c, CLS_ATTN, 0, static_cast<double>(L) * L * 6,
+             [=](cudaStream_t s) { return launch_softmax_rows(ps, L, L, scale, pp, s); });
+        push(c, CLS_ATTN, 0, static_cast<double>(L) * C * 4,
+             [=](cudaStream_t s) { return launch_transpose_bf16(q + 2 * C, 3 * C, L, C, pvt, s); });
+        // out_i = sum_j p_ij v_j : A = P [L][L], "weights" = V^T [C][L]
+        if (!make_gemm_plan(&p, pp, L, L, nullptr, 0, pvt, C, OUT_BF16, c.ptr<bf16>(o) + static_cast<size_t>(n) * L * C, C,
+                            nullptr, nullptr, 1, 0, nullptr, 0))
+          return false;
+        {
+          GemmPlan copy = p;
+          push(c, CLS_ATTN, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+        }
+      }
+      if (!make_gemm_plan(&p, c.ptr<bf16>(o), static_cast<int>(M), C, nullptr, 0, w.wo, C, OUT_F32, c.ptr<float>(*out), C, w.bo,
+                          nullptr, 1, 0, c.ptr<float>(x), C))
+        return false;
+      GemmPlan copy = p;
+      push(c, CLS_LINEAR, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+    }
+    c.release(a);
+    c.release(qkv);
+    c.release(o);
+    c.release(sc);
+    c.release(pr);
+    c.release(vt);
+    return true;
+  }
+
+  // Upsample (model.py:71-76): nearest 2x + conv3x3, folded into four 2x2-tap phase convs
+  bool plan_up(Ctx& c, const VConv& w, const Buf& x, int H, int W, Buf* out) {
+    const int C = w.cin;
+    Buf xb = c.alloc(x.M, C, 2);
+    *out = c.alloc(static_cast<size_t>(x.M) * 4, w.cout, 4);
+    if (!c.dry) {
+      const float* px = c.ptr<float>(x);
+      bf16* pb = c.ptr<bf16>(xb);
+      const size_t n = static_cast<size_t>(x.M) * C;
+      push(c, CLS_OTHER, 0, static_cast<double>(n) * 6, [=](cudaStream_t s) { return launch_cast_bf16(px, n, pb, s); });
+      for (int phase = 0; phase < 4; ++phase) {
+        GemmPlan p;
+        ConvGeom g{c.n_img, H, W, 4, 1};
+        g.up_phase = phase;
+        if (!make_conv_plan(&p, pb, g, C, nullptr, 0, w.w + static_cast<size_t>(phase) * w.cout * 4 * C, w.cout, OUT_F32,
+                            c.ptr<float>(*out), w.cout, w.b, nullptr, 1, 0, nullptr, 0))
+          return false;
+        p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C;  // algorithmic: the un-folded conv's share
+        GemmPlan copy = p;
+        push(c, CLS_CONV, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+      }
+    }
+    c.release(xb);
+    return true;
+  }
+
+  bool build_plan(Ctx& c, int N, int H, int W) {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (N < 1 || !pow2(H) || !pow2(W)) {
+      set_error("vae: latent H and W must be powers of two");
+      return false;
+    }
+    c.n_img = N;
+    Buf gnp;
+    gnp.bytes = groupnorm_partial_bytes(N);
+    gnp.off = c.arena.alloc(gnp.bytes);
+    gnp.valid = true;
+    if (!c.dry) {
+      c.gn_partial = c.ptr<float>(gnp);
+      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(N), 0, gnp.bytes - groupnorm_sync_offset(N)));
+    }
+    const size_t M0 = static_cast<size_t>(N) * H * W;
+    Buf a0 = c.alloc(M0, kpad_in, 2);
+    Buf h = c.alloc(M0, c_in, 4);
+    if (!c.dry) {
+      Vae* self = this;
+      bf16* pa0 = c.ptr<bf16>(a0);
+      const int zc = cfg.z_channels, kp = kpad_in;
+      const float *wpq = w_pq, *bpq = b_pq;
+      push(c, CLS_OTHER, 0, static_cast<double>(M0) * (kp * 2 + zc * 4), [=](cudaStream_t s) {
+        return launch_vae_input_pack(self->io_z, N, zc, H, W, wpq, bpq, self->io_inv_scale, kp, pa0, s);
+      });
+      GemmPlan p;
+      if (!make_gemm_plan(&p, pa0, static_cast<int>(M0), kp, nullptr, 0, w_in, c_in, OUT_F32, c.ptr<float>(h), c_in, b_in,
+                          nullptr, 1, 0, nullptr, 0))
+        return false;
+      GemmPlan copy = p;
+      push(c, CLS_LINEAR, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+    }
+    c.release(a0);
+    Buf cur = h;
+    int curH = H, curW = W;
+    for (const VLayer& l : layers) {
+      Buf nxt;
+      if (l.kind == V_RES) {
+        if (!plan_res(c, res[l.idx], cur, curH, curW, &nxt)) return false;
+      } else if (l.kind == V_ATTN) {
+        if (!plan_attn(c, attn[l.idx], cur, curH, curW, &nxt)) return false;
+      } else {
+        if (!plan_up(c, up[l.idx], cur, curH, curW, &nxt)) return false;
+        curH *= 2;
+        curW *= 2;
+      }
+      c.release(cur);
+      cur = nxt;
+    }
+    // norm_out, swish, conv_out (model.py:633-637)
+    const size_t Mo = static_cast<size_t>(N) * curH * curW;
+    Buf a = c.alloc(Mo, c_last, 2);
+    if (!op_gn(c, cur, curH * curW, out_gn_g, out_gn_b, 1, a, nullptr)) return false;
+    c.release(cur);
+    Buf o32 = c.alloc(Mo, 32, 4);
+    if (!c.dry) {
+      if (!conv_op(c, c.ptr<bf16>(a), curH, curW, c_last, nullptr, 0, w_out, 32, c.ptr<float>(o32), b_out, nullptr)) return false;
+      Vae* self = this;
+      const float* po = c.ptr<float>(o32);
+      const int cout = cfg.out_ch, oh = curH, ow = curW;
+      push(c, CLS_OTHER, 0, static_cast<double>(Mo) * cout * 8,
+           [=](cudaStream_t s) { return launch_vae_output(po, 32, N, cout, oh, ow, self->io_out, s); });
+    }
+    c.release(a);
+    c.release(o32);
+    return true;
+  }
+
+  bool workspace_bytes(int N, int H, int W, size_t* bytes) {
+    Ctx c;
+    c.dry = true;
+    std::vector<Op> dummy;
+    c.ops = &dummy;
+    if (!build_plan(c, N, H, W)) return false;
+    *bytes = c.arena.peak + 1024;
+    return true;
+  }
+
+  bool decode(const float* z, float* out, int N, int H, int W, float scale_factor, void* ws, size_t ws_bytes,
+              cudaStream_t stream) {
+    if (!finalized) {
+      set_error("cap4d_b200_vae_finalize has not been called");
+      return false;
+    }
+    if (!(N == pN && H == pH && W == pW && ws == p_ws && ws_bytes == p_ws_bytes && !ops.empty())) {
+      size_t need = 0;
+      if (!workspace_bytes(N, H, W, &need)) return false;
+      if (ws == nullptr || ws_bytes < need) {
+        set_error("workspace too small: need " + std::to_string(need) + " bytes");
+        return false;
+      }
+      ops.clear();
+      Ctx c;
+      c.dry = false;
+      c.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+      c.ops = &ops;
+      if (!build_plan(c, N, H, W)) {
+        ops.clear();
+        return false;
+      }
+      pN = N, pH = H, pW = W, p_ws = ws, p_ws_bytes = ws_bytes;
+    }
+    io_z = z;
+    io_out = out;
+    io_inv_scale = 1.0f / scale_factor;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      cudaError_t e = ops[i].run(stream);
+      if (e != cudaSuccess) {
+        set_error("vae: launch of op " + std::to_string(i) + " failed: " + cudaGetErrorString(e) + " / " + get_error());
+        return false;
+      }
+    }
+    return true;
+  }
+};
+
+}  // namespace
+
+}  // namespace cap4d
+
+using namespace cap4d;
+
+extern "C" {
+
+int cap4d_b200_vae_create(const cap4d_b200_vae_config* cfg, void** handle) {
+  if (cfg == nullptr || handle == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  Vae* v = new Vae();
+  v->cfg = *cfg;
+  if (!v->build_topology()) {
+    delete v;
+    return 2;
+  }
+  *handle = v;
+  return 0;
+}
+
+int cap4d_b200_vae_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || name == nullptr || data == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  if (v->finalized) {
+    set_error("weights are already finalized");
+    return 1;
+  }
+  RawTensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    t.numel *= static_cast<size_t>(shape[i]);
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&t.d), std::max<size_t>(t.numel * sizeof(float), 16)) != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed for ") + name);
+    return 3;
+  }
+  cudaError_t e = cudaMemcpy(t.d, data, t.numel * sizeof(float), cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaFree(t.d);
+    set_error(std::string("cudaMemcpy failed for ") + name + ": " + cudaGetErrorString(e));
+    return 3;
+  }
+  auto it = v->raw.find(name);
+  if (it != v->raw.end() && it->second.d) cudaFree(it->second.d);
+  v->raw[name] = t;
+  return 0;
+}
+
+int cap4d_b200_vae_num_params(void* handle, int* n) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *n = static_cast<int>(v->expected_params().size());
+  return 0;
+}
+
+int cap4d_b200_vae_param_info(void* handle, int index, char* name, int name_cap, int64_t* shape, int* ndim) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || name == nullptr || shape == nullptr || ndim == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  auto params = v->expected_params();
+  if (index < 0 || index >= static_cast<int>(params.size())) {
+    set_error("parameter index out of range");
+    return 1;
+  }
+  snprintf(name, name_cap, "%s", params[index].first.c_str());
+  *ndim = static_cast<int>(params[index].second.size());
+  for (int i = 0; i < *ndim; ++i) shape[i] = params[index].second[i];
+  return 0;
+}
+
+int cap4d_b200_vae_finalize(void* handle) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  return v->finalize() ? 0 : 4;
+}
+
+int cap4d_b200_vae_workspace_bytes(void* handle, int N, int H, int W, size_t* bytes) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || bytes == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  return v->workspace_bytes(N, H, W, bytes) ? 0 : 5;
+}
+
+int cap4d_b200_vae_decode(void* handle, const float* z, float* images, int N, int H, int W, float scale_factor,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || z == nullptr || images == nullptr || scale_factor == 0.f) {
+    set_error("null argument");
+    return 1;
+  }
+  return v->decode(z, images, N, H, W, scale_factor, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)) ? 0 : 6;
+}
+
+int cap4d_b200_vae_num_launches(void* handle, int* n) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *n = static_cast<int>(v->ops.size());
+  return 0;
+}
+
+int cap4d_b200_vae_destroy(void* handle) {
+  delete static_cast<Vae*>(handle);
+  return 0;
+}
+
+}  // extern "C"

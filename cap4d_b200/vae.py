@@ -1,0 +1,174 @@
+"""B200 VAE decoder: the reference's `decode_first_stage` (controlnet/ldm/models/diffusion/ddpm.py:822-830 ->
+AutoencoderKL.decode, controlnet/ldm/models/autoencoder.py:87-91) behind the same call, on libcap4d_b200.so.
+
+    vae = B200VAEDecoder.from_reference(model.first_stage_model, scale_factor=model.scale_factor)
+    images = vae.decode_first_stage(latents)          # [N, 4, h, w] -> [N, 3, 8h, 8w], about [-1, 1]
+
+`cap4d/inference/utils.py:131-137` decodes the generated views one at a time; this decodes `batch` views per
+launch plan.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _lib
+
+# first_stage_config of configs/mmdm/cap4d_mmdm_final.yaml:117-137
+VAE_CONFIG = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, embed_dim=4, out_ch=3)
+SCALE_FACTOR = 0.18215
+
+
+def _make_config(cfg: Mapping) -> _lib.VaeConfig:
+    c = _lib.VaeConfig()
+    c.ch = int(cfg["ch"])
+    mult = list(cfg["ch_mult"])
+    if len(mult) > _lib.MAX_LEVELS:
+        raise ValueError("too many levels")
+    c.n_levels = len(mult)
+    for i, m in enumerate(mult):
+        c.ch_mult[i] = int(m)
+    c.num_res_blocks = int(cfg["num_res_blocks"])
+    c.z_channels = int(cfg["z_channels"])
+    c.embed_dim = int(cfg.get("embed_dim", cfg["z_channels"]))
+    c.out_ch = int(cfg["out_ch"])
+    return c
+
+
+class B200VAEDecoder(torch.nn.Module):
+    def __init__(self, config: Mapping, state_dict: Mapping[str, torch.Tensor], scale_factor: float = SCALE_FACTOR,
+                 device: Optional[torch.device] = None):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cap4d_b200: a CUDA device (B200, sm_100a) is required; there is no CPU path")
+        self.config = dict(config)
+        self.scale_factor = float(scale_factor)
+        self._device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._lib = _lib.load()
+        self._handle = ctypes.c_void_p()
+        self._ws: Dict = {}
+        cfg = _make_config(config)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.cap4d_b200_vae_create(ctypes.byref(cfg), ctypes.byref(self._handle)), "vae_create")
+            for name, t in state_dict.items():
+                if not name.startswith(("decoder.", "post_quant_conv.")):
+                    continue  # encoder / quant_conv / loss entries of a full AutoencoderKL state_dict
+                t32 = t.detach().to(dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(1, t32.dim()))(*t32.shape)
+                _lib.check(self._lib.cap4d_b200_vae_load_weight(self._handle, name.encode(),
+                                                               ctypes.c_void_p(t32.data_ptr()), shape, t32.dim()),
+                           f"vae_load_weight({name})")
+            _lib.check(self._lib.cap4d_b200_vae_finalize(self._handle), "vae_finalize")
+
+    @staticmethod
+    def param_shapes(config: Mapping) -> Dict[str, tuple]:
+        """state_dict keys -> shapes the decoder needs (host-only; no GPU needed)."""
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        cfg = _make_config(config)
+        _lib.check(lib.cap4d_b200_vae_create(ctypes.byref(cfg), ctypes.byref(h)), "vae_create")
+        try:
+            n = ctypes.c_int()
+            _lib.check(lib.cap4d_b200_vae_num_params(h, ctypes.byref(n)), "vae_num_params")
+            out = {}
+            name = ctypes.create_string_buffer(256)
+            shape = (ctypes.c_int64 * 4)()
+            nd = ctypes.c_int()
+            for i in range(n.value):
+                _lib.check(lib.cap4d_b200_vae_param_info(h, i, name, 256, shape, ctypes.byref(nd)), "vae_param_info")
+                out[name.value.decode()] = tuple(int(shape[k]) for k in range(nd.value))
+            return out
+        finally:
+            lib.cap4d_b200_vae_destroy(h)
+
+    @classmethod
+    def random_init(cls, config: Mapping = VAE_CONFIG, seed: int = 0, device=None) -> "B200VAEDecoder":
+        """Synthetic weights of the right architecture, generated on the GPU (benchmarks; no checkpoint offline)."""
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd = {}
+        for name, shape in cls.param_shapes(config).items():
+            if "norm" in name and name.endswith("weight"):
+                t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=dev)
+            elif name.endswith("bias"):
+                t = 0.05 * torch.randn(shape, generator=g, device=dev)
+            else:
+                fan_in = shape[1] * shape[2] * shape[3]
+                t = torch.randn(shape, generator=g, device=dev) / fan_in ** 0.5
+            sd[name] = t
+        return cls(config, sd, device=dev)
+
+    @classmethod
+    def from_reference(cls, first_stage_model, scale_factor: float = SCALE_FACTOR, device=None) -> "B200VAEDecoder":
+        dec = first_stage_model.decoder
+        cfg = dict(ch=dec.ch, ch_mult=tuple(m for m in _ch_mult(dec)), num_res_blocks=dec.num_res_blocks,
+                   z_channels=dec.conv_in.in_channels, embed_dim=first_stage_model.post_quant_conv.in_channels,
+                   out_ch=dec.conv_out.out_channels)
+        return cls(cfg, first_stage_model.state_dict(), scale_factor=scale_factor, device=device)
+
+    def __deepcopy__(self, memo):
+        raise RuntimeError("B200VAEDecoder is bound to one GPU: build one instance per device instead of deepcopy")
+
+    @property
+    def device(self):
+        return self._device
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.cap4d_b200_vae_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _workspace(self, N, H, W) -> torch.Tensor:
+        key = (N, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            self._ws.clear()  # the library keeps one plan
+            n = ctypes.c_size_t()
+            _lib.check(self._lib.cap4d_b200_vae_workspace_bytes(self._handle, N, H, W, ctypes.byref(n)), "vae_workspace")
+            ws = torch.empty(n.value + 2048, dtype=torch.uint8, device=self._device)
+            self._ws[key] = ws
+        return ws
+
+    @torch.no_grad()
+    def decode_first_stage(self, z: torch.Tensor, batch: int = 4) -> torch.Tensor:
+        """z: [N, 4, h, w] (or the reference's [N, V, 4, h, w]) sampler latents -> images like the reference's
+        decode_first_stage; `batch` latents per launch plan."""
+        lead = None
+        if z.dim() == 5:
+            lead = z.shape[:2]
+            z = z.reshape(-1, *z.shape[2:])
+        if z.dim() != 4 or z.shape[1] != self.config["z_channels"]:
+            raise ValueError("z must be [N, z_channels, h, w]")
+        zs = z.to(device=self._device, dtype=torch.float32).contiguous()
+        N, _, H, W = zs.shape
+        out = torch.empty((N, self.config["out_ch"], 8 * H, 8 * W), dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            i = 0
+            while i < N:
+                n = min(batch, N - i)
+                ws = self._workspace(n, H, W)
+                _lib.check(
+                    self._lib.cap4d_b200_vae_decode(self._handle, zs[i:i + n].data_ptr(), out[i:i + n].data_ptr(), n, H, W,
+                                                    self.scale_factor, ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
+                    "vae_decode")
+                i += n
+        out = out.to(z.device) if z.device != out.device else out
+        return out.reshape(*lead, *out.shape[1:]) if lead is not None else out
+
+    forward = decode_first_stage
+
+    def num_launches(self) -> int:
+        n = ctypes.c_int()
+        _lib.check(self._lib.cap4d_b200_vae_num_launches(self._handle, ctypes.byref(n)), "vae_num_launches")
+        return n.value
+
+
+def _ch_mult(decoder):
+    """ch_mult of a reference Decoder (it only stores ch and the built blocks): out channels of each level's
+    last block / ch, lowest resolution last (model.py:583-600)."""
+    return [decoder.up[lvl].block[-1].out_channels // decoder.ch for lvl in range(decoder.num_resolutions)]

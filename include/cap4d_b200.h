@@ -146,6 +146,36 @@ int cap4d_b200_groupnorm_bf16(const float* x1, int C1, const float* x2, int C2, 
 int cap4d_b200_layernorm_bf16(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
                               uint16_t* out, void* stream, float* ms_out, int iters);
 
+/* ---- VAE decoder handle: replaces MMLDM.decode_first_stage -----------------------------
+ * controlnet/ldm/models/diffusion/ddpm.py:822-830 (z / scale_factor) -> AutoencoderKL.decode
+ * (controlnet/ldm/models/autoencoder.py:87-91) -> Decoder.forward (controlnet/ldm/modules/diffusionmodules/
+ * model.py:606-640), called once per generated view by cap4d/inference/utils.py:131-133. */
+typedef struct cap4d_b200_vae_config {
+  int ch;               /* 128 */
+  int n_levels;         /* len(ch_mult) = 4 */
+  int ch_mult[CAP4D_B200_MAX_LEVELS]; /* 1,2,4,4 */
+  int num_res_blocks;   /* 2 */
+  int z_channels;       /* 4 */
+  int embed_dim;        /* 4 */
+  int out_ch;           /* 3 */
+} cap4d_b200_vae_config;
+
+/* Decoder.__init__ (model.py:546-604): derive the layer list (attn_resolutions = [] : mid-block attention only). */
+int cap4d_b200_vae_create(const cap4d_b200_vae_config* cfg, void** handle);
+/* fp32 parameters under the reference's state_dict names ("decoder.*", "post_quant_conv.*"; encoder entries
+ * are not needed); host or device pointers. */
+int cap4d_b200_vae_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim);
+int cap4d_b200_vae_num_params(void* handle, int* n);
+int cap4d_b200_vae_param_info(void* handle, int index, char* name, int name_cap, int64_t* shape, int* ndim);
+int cap4d_b200_vae_finalize(void* handle);
+int cap4d_b200_vae_workspace_bytes(void* handle, int N, int H, int W, size_t* bytes);
+/* z: fp32 [N][z_channels][H][W] (sampler latents, still multiplied by scale_factor);
+ * images: fp32 [N][out_ch][8H][8W] in about [-1, 1] (what decode_first_stage returns). */
+int cap4d_b200_vae_decode(void* handle, const float* z, float* images, int N, int H, int W, float scale_factor,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int cap4d_b200_vae_num_launches(void* handle, int* n);
+int cap4d_b200_vae_destroy(void* handle);
+
 const char* cap4d_b200_last_error(void);
 const char* cap4d_b200_version(void);
 

@@ -21,8 +21,8 @@ import torch.nn.functional as F
 
 # first_stage_config of configs/mmdm/cap4d_mmdm_final.yaml:117-137
 PRODUCTION_VAE = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3, embed_dim=4)
-# same topology, 1/4 of the channels (GroupNorm needs multiples of 32)
-TINY_VAE = dict(ch=32, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3, embed_dim=4)
+# same topology, half the channels (the conv kernel's K blocks need input channels in multiples of 64)
+TINY_VAE = dict(ch=64, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3, embed_dim=4)
 SCALE_FACTOR = 0.18215  # cap4d_mmdm_final.yaml: scale_factor
 
 

@@ -117,6 +117,8 @@ def test_gemm_tile_configurations_agree(ops, cuda_device, monkeypatch):
         (5, 4, 4, 64, 64),       # tile = 8 images, image tail -> OOB zero fill
         (8, 2, 2, 64, 32),       # lowest level of the tiny test model
         (16, 8, 8, 1280, 1280),  # production level-3 shape
+        (1, 8, 256, 64, 64),     # image row wider than a tile (VAE decoder at 256 / 512 pixels): 2 tiles per row
+        (2, 4, 512, 128, 32),    # 4 tiles per row
     ],
 )
 def test_conv3x3_stride1(ops, cuda_device, n_img, H, W, Cin, Cout):

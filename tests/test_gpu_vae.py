@@ -1,0 +1,91 @@
+"""VAE decode on the GPU, through the C ABI, against the committed fixtures the unmodified
+reference AutoencoderKL produced and against the oracle on the same seeded inputs.
+
+Tolerance: the decoder's output is an image in about [-1, 1] that the reference quantises to uint8
+(cap4d/inference/utils.py:134-137, step 2/255 = 7.8e-3): max|a-b|/max|b| <= 2e-2 with bf16 operands and
+PSNR >= 40 dB (peak = the reference image's range)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmdm_oracle as O
+from oracle import vae_oracle as VO
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def tiny_vaes(cuda_device):
+    from cap4d_b200 import B200VAEDecoder
+
+    cache = {}
+
+    def get(seed):
+        if seed not in cache:
+            sd = VO.init_vae_state_dict(VO.TINY_VAE, seed=seed)
+            cache[seed] = (B200VAEDecoder(VO.TINY_VAE, sd, device=cuda_device), sd)
+        return cache[seed]
+
+    return get
+
+
+@pytest.mark.parametrize("name", ["vae_tiny_h8", "vae_tiny_h16x8"])
+def test_vae_matches_reference_fixture(cuda_device, tiny_vaes, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    vae, _ = tiny_vaes(int(g["wseed"]))
+    z = torch.randn(int(g["N"]), 4, int(g["H"]), int(g["W"]), generator=torch.Generator().manual_seed(int(g["zseed"]))) * 0.8
+    y = vae.decode_first_stage(z.to(cuda_device)).cpu()
+    ref = torch.from_numpy(g["out"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    err, p = O.max_rel_err(y, ref), O.psnr(y, ref)
+    print(f"{name}: max-rel {err:.3e} PSNR {p:.1f} dB")
+    assert err < TOL and p >= 40.0
+
+
+@pytest.mark.parametrize("N,H,W,batch", [(3, 16, 16, 2), (1, 32, 32, 1), (5, 8, 8, 4), (1, 64, 32, 1)])
+def test_vae_matches_oracle(cuda_device, tiny_vaes, N, H, W, batch):
+    # 32x32 / 64x32 latents: 256- and 512-pixel-wide feature maps (image rows wider than a 128-pixel tile)
+    vae, sd = tiny_vaes(0)
+    z = torch.randn(N, 4, H, W, generator=torch.Generator().manual_seed(N * 100 + H)) * 0.8
+    ref = VO.vae_decode(sd, VO.TINY_VAE, z)
+    y = vae.decode_first_stage(z.to(cuda_device), batch=batch).cpu()
+    err, p = O.max_rel_err(y, ref), O.psnr(y, ref)
+    print(f"N{N} {H}x{W}: max-rel {err:.3e} PSNR {p:.1f} dB")
+    assert y.shape == (N, 3, 8 * H, 8 * W) and err < TOL and p >= 40.0
+    # uint8 images as written by the reference (utils.py:134-137): off by at most one level almost everywhere
+    a, b = VO.to_uint8_bgr(y).int(), VO.to_uint8_bgr(ref).int()
+    assert float(((a - b).abs() <= 2).float().mean()) > 0.999
+
+
+def test_vae_call_conventions(cuda_device, tiny_vaes):
+    vae, sd = tiny_vaes(0)
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(3))
+    y4 = vae.decode_first_stage(z.to(cuda_device))
+    y5 = vae.decode_first_stage(z[None].to(cuda_device))       # the reference passes [1, n, 4, h, w] (utils.py:133)
+    assert y5.shape == (1, 2, 3, 64, 64) and torch.equal(y5[0], y4)
+    assert torch.equal(vae.decode_first_stage(z.to(cuda_device)), y4)  # fixed plan, fixed reduction order
+    assert vae.decode_first_stage(z).device.type == "cpu"       # comes back on the caller's device
+    with pytest.raises(ValueError):
+        vae.decode_first_stage(torch.zeros(1, 3, 8, 8))
+
+
+def test_vae_production_config(cuda_device):
+    """first_stage_config of cap4d_mmdm_final.yaml (ch 128, 49.5 M decoder parameters): one 64x64 latent -> 512x512.
+    Checker: the oracle evaluated on the GPU in fp32 (TF32 off)."""
+    from cap4d_b200 import B200VAEDecoder
+
+    cfg = VO.PRODUCTION_VAE
+    sd = VO.init_vae_state_dict(cfg, seed=0)
+    vae = B200VAEDecoder(cfg, sd, device=cuda_device)
+    z = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(11)) * 0.8
+    y = vae.decode_first_stage(z.to(cuda_device), batch=2)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = VO.vae_decode({k: v.to(cuda_device) for k, v in sd.items()}, cfg, z.to(cuda_device))
+    err, p = O.max_rel_err(y.cpu(), ref.cpu()), O.psnr(y.cpu(), ref.cpu())
+    print(f"production VAE decode 2 x 512x512: max-rel {err:.3e} PSNR {p:.1f} dB, {vae.num_launches()} launches")
+    assert y.shape == (2, 3, 512, 512) and err < TOL and p >= 40.0
