@@ -102,11 +102,8 @@ class B200VAEDecoder(torch.nn.Module):
 
     @classmethod
     def from_reference(cls, first_stage_model, scale_factor: float = SCALE_FACTOR, device=None) -> "B200VAEDecoder":
-        dec = first_stage_model.decoder
-        cfg = dict(ch=dec.ch, ch_mult=tuple(m for m in _ch_mult(dec)), num_res_blocks=dec.num_res_blocks,
-                   z_channels=dec.conv_in.in_channels, embed_dim=first_stage_model.post_quant_conv.in_channels,
-                   out_ch=dec.conv_out.out_channels)
-        return cls(cfg, first_stage_model.state_dict(), scale_factor=scale_factor, device=device)
+        return cls(config_from_reference(first_stage_model), first_stage_model.state_dict(), scale_factor=scale_factor,
+                   device=device)
 
     def __deepcopy__(self, memo):
         raise RuntimeError("B200VAEDecoder is bound to one GPU: build one instance per device instead of deepcopy")
@@ -166,6 +163,22 @@ class B200VAEDecoder(torch.nn.Module):
         n = ctypes.c_int()
         _lib.check(self._lib.cap4d_b200_vae_num_launches(self._handle, ctypes.byref(n)), "vae_num_launches")
         return n.value
+
+
+def config_from_reference(first_stage_model) -> Dict:
+    """Decoder configuration of a reference AutoencoderKL (controlnet/ldm/models/autoencoder.py:14-45)."""
+    dec = first_stage_model.decoder
+    return dict(ch=dec.ch, ch_mult=tuple(_ch_mult(dec)), num_res_blocks=dec.num_res_blocks,
+                z_channels=dec.conv_in.in_channels, embed_dim=first_stage_model.post_quant_conv.in_channels,
+                out_ch=dec.conv_out.out_channels)
+
+
+def install_vae(mmldm, device=None) -> B200VAEDecoder:
+    """Route `mmldm.decode_first_stage` (cap4d/mmdm/mmdm.py:99-103 -> ddpm.py:822-830) through the B200 decoder:
+    replaces `mmldm.first_stage_model.decode` in place.  ddpm.py has already divided by scale_factor there."""
+    vae = B200VAEDecoder.from_reference(mmldm.first_stage_model, scale_factor=1.0, device=device)
+    mmldm.first_stage_model.decode = vae.decode_first_stage
+    return vae
 
 
 def _ch_mult(decoder):

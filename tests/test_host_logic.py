@@ -216,3 +216,19 @@ def test_sampler_two_ranks_gloo(tmp_path, name):
     _, ref = _run_sampler(name, 1)
     assert torch.equal(z0, z1)  # every rank holds the full, identical latent store after each exchange
     assert O.max_rel_err(z0, ref) < 1e-4
+
+
+def test_vae_config_from_reference_module():
+    """The decoder configuration is read off a reference AutoencoderKL (only where the reference is present)."""
+    from oracle import ref_import as RI
+    from oracle import vae_oracle as VO
+
+    if not RI.reference_available():
+        pytest.skip("reference sources not present (GPU box)")
+    from cap4d_b200.vae import B200VAEDecoder, config_from_reference
+
+    vae = RI.build_reference_vae(VO.TINY_VAE)
+    cfg = config_from_reference(vae)
+    assert cfg == dict(VO.TINY_VAE, ch_mult=tuple(VO.TINY_VAE["ch_mult"]))
+    want = {k: tuple(v.shape) for k, v in vae.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    assert B200VAEDecoder.param_shapes(cfg) == want
