@@ -231,6 +231,21 @@ __global__ void vae_output_kernel(const float* __restrict__ h, int ldh, int n_im
   }
 }
 
+// h fp32 NHWC [n*H*W][ldh] (first 3 columns = R, G, B in [-1, 1]) -> uint8 HWC with the channels reversed,
+// exactly the array the reference hands to cv2.imwrite (cap4d/inference/utils.py:134-137):
+// ((x + 1) / 2).clip(0, 1) * 255 truncated to uint8, channels [2, 1, 0].
+__global__ void vae_output_u8_kernel(const float* __restrict__ h, int ldh, size_t n_pix, unsigned char* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_pix;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __fdiv_rn(__fadd_rn(h[i * ldh + (2 - c)], 1.0f), 2.0f);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      out[i * 3 + c] = static_cast<unsigned char>(__fmul_rn(v, 255.0f));
+    }
+  }
+}
+
 // softmax over the rows of fp32 scores [rows][L] (times scale) -> bf16 probabilities; one block per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int L, float scale,
                                                            bf16* __restrict__ p) {
@@ -505,6 +520,11 @@ cudaError_t launch_vae_output(const float* h, int ldh, int n_img, int cout, int 
                               cudaStream_t stream) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
   vae_output_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, n_img, cout, H, W, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vae_output_u8(const float* h, int ldh, size_t n_pix, unsigned char* out, cudaStream_t stream) {
+  vae_output_u8_kernel<<<grid_for(n_pix, 256), 256, 0, stream>>>(h, ldh, n_pix, out);
   return cudaGetLastError();
 }
 

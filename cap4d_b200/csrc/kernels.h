@@ -178,6 +178,8 @@ cudaError_t launch_vae_input_pack(const float* z, int n_img, int zc, int H, int 
 // fp32 NHWC [n*H*W][ldh] -> fp32 NCHW [n][cout][H][W]
 cudaError_t launch_vae_output(const float* h, int ldh, int n_img, int cout, int H, int W, float* out,
                               cudaStream_t stream);
+// fp32 NHWC [n_pix][ldh] (R, G, B first) -> uint8 [n_pix][3] = BGR of ((x + 1) / 2).clip(0, 1) * 255, truncated
+cudaError_t launch_vae_output_u8(const float* h, int ldh, size_t n_pix, unsigned char* out, cudaStream_t stream);
 // softmax(scale * s) over rows of fp32 [rows][L] -> bf16
 cudaError_t launch_softmax_rows(const float* s, int rows, int L, float scale, bf16* p, cudaStream_t stream);
 // dst[cols][rows] = src[rows][cols] (src row stride ld)

@@ -62,7 +62,8 @@ struct Vae {
   // plan
   std::vector<Op> ops;
   const float* io_z = nullptr;
-  float* io_out = nullptr;
+  float* io_out = nullptr;         // fp32 NCHW images, or
+  unsigned char* io_out_u8 = nullptr;  // uint8 HWC BGR images (exactly one of the two is set per call)
   float io_inv_scale = 1.f;
   int pN = 0, pH = 0, pW = 0;
   void* p_ws = nullptr;
@@ -521,8 +522,10 @@ struct Vae {
       Vae* self = this;
       const float* po = c.ptr<float>(o32);
       const int cout = cfg.out_ch, oh = curH, ow = curW;
-      push(c, CLS_OTHER, 0, static_cast<double>(Mo) * cout * 8,
-           [=](cudaStream_t s) { return launch_vae_output(po, 32, N, cout, oh, ow, self->io_out, s); });
+      push(c, CLS_OTHER, 0, static_cast<double>(Mo) * cout * 8, [=](cudaStream_t s) {
+        if (self->io_out_u8 != nullptr) return launch_vae_output_u8(po, 32, Mo, self->io_out_u8, s);
+        return launch_vae_output(po, 32, N, cout, oh, ow, self->io_out, s);
+      });
     }
     c.release(a);
     c.release(o32);
@@ -539,8 +542,12 @@ struct Vae {
     return true;
   }
 
-  bool decode(const float* z, float* out, int N, int H, int W, float scale_factor, void* ws, size_t ws_bytes,
-              cudaStream_t stream) {
+  bool decode(const float* z, float* out, unsigned char* out_u8, int N, int H, int W, float scale_factor, void* ws,
+              size_t ws_bytes, cudaStream_t stream) {
+    if (out_u8 != nullptr && cfg.out_ch != 3) {
+      set_error("vae: uint8 BGR output needs out_ch == 3");
+      return false;
+    }
     if (!finalized) {
       set_error("cap4d_b200_vae_finalize has not been called");
       return false;
@@ -565,6 +572,7 @@ struct Vae {
     }
     io_z = z;
     io_out = out;
+    io_out_u8 = out_u8;
     io_inv_scale = 1.0f / scale_factor;
     for (size_t i = 0; i < ops.size(); ++i) {
       cudaError_t e = ops[i].run(stream);
@@ -684,7 +692,23 @@ int cap4d_b200_vae_decode(void* handle, const float* z, float* images, int N, in
     set_error("null argument");
     return 1;
   }
-  return v->decode(z, images, N, H, W, scale_factor, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)) ? 0 : 6;
+  return v->decode(z, images, nullptr, N, H, W, scale_factor, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream))
+             ? 0
+             : 6;
+}
+
+int cap4d_b200_vae_decode_u8(void* handle, const float* z, uint8_t* images_bgr, int N, int H, int W, float scale_factor,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  Vae* v = static_cast<Vae*>(handle);
+  if (v == nullptr || z == nullptr || images_bgr == nullptr || scale_factor == 0.f) {
+    set_error("null argument");
+    return 1;
+  }
+  return v->decode(z, nullptr, images_bgr, N, H, W, scale_factor, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream))
+             ? 0
+             : 6;
 }
 
 int cap4d_b200_vae_num_launches(void* handle, int* n) {

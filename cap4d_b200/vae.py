@@ -131,6 +131,28 @@ class B200VAEDecoder(torch.nn.Module):
         return ws
 
     @torch.no_grad()
+    def decode_to_uint8_bgr(self, z: torch.Tensor, batch: int = 8) -> torch.Tensor:
+        """z [N, 4, h, w] -> uint8 [N, 8h, 8w, 3] on the host: the arrays `convert_and_save_latent_images`
+        (cap4d/inference/utils.py:131-137) passes to cv2.imwrite, converted on the device (a quarter of the bytes
+        of the fp32 images cross PCIe)."""
+        if z.dim() != 4 or z.shape[1] != self.config["z_channels"]:
+            raise ValueError("z must be [N, z_channels, h, w]")
+        zs = z.to(device=self._device, dtype=torch.float32).contiguous()
+        N, _, H, W = zs.shape
+        out = torch.empty((N, 8 * H, 8 * W, 3), dtype=torch.uint8, device=self._device)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            for i in range(0, N, batch):
+                n = min(batch, N - i)
+                ws = self._workspace(n, H, W)
+                _lib.check(
+                    self._lib.cap4d_b200_vae_decode_u8(self._handle, zs[i:i + n].data_ptr(), out[i:i + n].data_ptr(), n, H,
+                                                       W, self.scale_factor, ws.data_ptr(), ws.numel(),
+                                                       ctypes.c_void_p(stream)),
+                    "vae_decode_u8")
+        return out.cpu()
+
+    @torch.no_grad()
     def decode_first_stage(self, z: torch.Tensor, batch: int = 4) -> torch.Tensor:
         """z: [N, 4, h, w] (or the reference's [N, V, 4, h, w]) sampler latents -> images like the reference's
         decode_first_stage; `batch` latents per launch plan."""

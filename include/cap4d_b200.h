@@ -173,6 +173,10 @@ int cap4d_b200_vae_workspace_bytes(void* handle, int N, int H, int W, size_t* by
  * images: fp32 [N][out_ch][8H][8W] in about [-1, 1] (what decode_first_stage returns). */
 int cap4d_b200_vae_decode(void* handle, const float* z, float* images, int N, int H, int W, float scale_factor,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Same decode, but the result is the uint8 array the reference writes to disk (cap4d/inference/utils.py:134-137):
+ * images_bgr: uint8 [N][8H][8W][3] = ((x + 1) / 2).clip(0, 1) * 255 truncated, channels reversed for cv2.imwrite. */
+int cap4d_b200_vae_decode_u8(void* handle, const float* z, uint8_t* images_bgr, int N, int H, int W, float scale_factor,
+                             void* workspace, size_t workspace_bytes, void* stream);
 int cap4d_b200_vae_num_launches(void* handle, int* n);
 int cap4d_b200_vae_destroy(void* handle);
 

@@ -73,6 +73,19 @@ def test_vae_call_conventions(cuda_device, tiny_vaes):
         vae.decode_first_stage(torch.zeros(1, 3, 8, 8))
 
 
+def test_vae_uint8_output_is_the_reference_conversion(cuda_device, tiny_vaes):
+    """decode_to_uint8_bgr == the reference's host-side conversion (utils.py:134-137) applied to this decoder's
+    own fp32 output, bit for bit; and within one or two levels of the oracle's image."""
+    vae, sd = tiny_vaes(0)
+    z = torch.randn(3, 4, 16, 16, generator=torch.Generator().manual_seed(9)) * 1.5   # some pixels clip
+    u8 = vae.decode_to_uint8_bgr(z, batch=2)
+    f32 = vae.decode_first_stage(z.to(cuda_device), batch=2).cpu()
+    assert u8.shape == (3, 128, 128, 3) and u8.dtype == torch.uint8
+    assert torch.equal(u8, VO.to_uint8_bgr(f32))
+    ref = VO.to_uint8_bgr(VO.vae_decode(sd, VO.TINY_VAE, z))
+    assert float(((u8.int() - ref.int()).abs() <= 2).float().mean()) > 0.999
+
+
 def test_vae_production_config(cuda_device):
     """first_stage_config of cap4d_mmdm_final.yaml (ch 128, 49.5 M decoder parameters): one 64x64 latent -> 512x512.
     Checker: the oracle evaluated on the GPU in fp32 (TF32 off)."""
