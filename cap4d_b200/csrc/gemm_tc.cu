@@ -89,6 +89,11 @@ __device__ __forceinline__ void epilogue_store_bf16(bf16* dst, const float* acc)
   }
 }
 
+__device__ __forceinline__ void load_vec32(float (&dst)[32], const float* __restrict__ src) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) ld_global_nc_v8(src + j, dst + j);
+}
+
 __device__ __forceinline__ void add_vec32(float* acc, const float* __restrict__ src) {
   float b[32];
 #pragma unroll
@@ -108,6 +113,9 @@ __device__ __forceinline__ int up_row(int row, int H, int W, int py, int px) {
 // A CTA tile is (msub * 128) x BN: msub in {1, 2} 128-row sub-tiles share one B (weight) tile per k-block,
 // which raises the FLOPs per byte streamed from L2 - the resource this kernel is bound by - from
 // 2*128*BN*64 / (16K + 128 BN) to 2*256*BN*64 / (32K + 128 BN).
+// EPI = 1: plain GEMM + fp32 residual (no conv operand, no GEGLU, no per-image bias): its own instantiation so
+// that the residual look-ahead buffers below do not disturb the register allocation of the generic epilogue.
+template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
@@ -266,10 +274,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_tile = tile - m_tile * p.tiles_n;
       const int acc = (p.n_acc == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
-      mbar_wait(&tail->tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
       auto chunk_col = [&](int cc) { return (cc / cps) * p.BN + (cc % cps) * tcols; };  // TMEM column of chunk cc
+      if constexpr (EPI == 1) {
+        // Plain GEMM + fp32 residual (to_out, FF2, proj_out: K is short, the kernel IS its epilogue, and ncu
+        // shows it waiting on the residual rows: ~4 KB in flight per warp).  The residual does not depend on
+        // the accumulator, so chunk cc+1's row segment is requested before chunk cc is even read from TMEM
+        // (the first one before the tile's MMAs have finished): two buffers, used alternately.
+        float r0[32], r1[32];
+        // (sub, c) of the chunk in hand and of the next one, advanced without dividing
+        int sub = c_begin / cps, c = c_begin - sub * cps;
+        const int row_lane = m_tile * p.msub * BM + q * 32 + lane;
+        const float* res_col = p.residual + n_tile * p.BN;
+        auto res_load = [&](int sb, int ch, float(&r)[32]) {
+          const int ri = row_lane + sb * BM;
+          if (ri < p.M) load_vec32(r, res_col + static_cast<size_t>(ri) * p.ldr + ch * 32);
+        };
+        if (c_begin < c_end) res_load(sub, c, r0);
+        mbar_wait(&tail->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        if (c_begin < c_end) tmem_ld32(taddr + sub * p.BN + c * 32, v);
+        auto process = [&](int cc, float(&cur)[32], float(&nxt)[32]) {
+          int sub_n = sub, c_n = c + 1;
+          if (c_n == cps) {
+            c_n = 0;
+            ++sub_n;
+          }
+          const bool more = cc + 1 < c_end;
+          if (more) res_load(sub_n, c_n, nxt);
+          tmem_ld_wait();
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+          if (more) tmem_ld32(taddr + sub_n * p.BN + c_n * 32, v);
+          const int row = row_lane + sub * BM;
+          if (row < p.M) {
+            const int col0 = n_tile * p.BN + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] += cur[j];
+            if (p.bias != nullptr) add_vec32(a, p.bias + col0);
+            if ((p.out_mode & 15) == OUT_F32) {
+              epilogue_store_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
+            } else {
+              epilogue_store_bf16(reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
+            }
+          }
+          sub = sub_n;
+          c = c_n;
+        };
+        for (int cc = c_begin; cc < c_end; cc += 2) {
+          process(cc, r0, r1);
+          if (cc + 1 < c_end) process(cc + 1, r1, r0);
+        }
+      } else {
+      mbar_wait(&tail->tmem_full[acc], acc_phase);
+      tc_fence_after();
       uint32_t v[32], vg[32];
       if (c_begin < c_end) {
         tmem_ld32(taddr + chunk_col(c_begin), v);
@@ -319,6 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }  // generic epilogue
       tc_fence_before();
       mbar_arrive(&tail->tmem_empty[acc]);
     }
@@ -962,10 +1023,19 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
   return autotune(plan, Wt, N, ntaps * Cin + K2);
 }
 
+// which problems take the EPI = 1 instantiation (see gemm_tc_kernel)
+static bool residual_lookahead(const GemmParams& p) {
+  static const bool off = getenv("CAP4D_GEMM_NO_LOOKAHEAD") != nullptr;
+  return !off && p.residual != nullptr && !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 &&
+         p.rowbias == nullptr && p.up_py < 0;
+}
+
 cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -973,8 +1043,10 @@ cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   }
   if (plan.two_cta)
     gemm_tc_2sm_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
+  else if (residual_lookahead(plan.p))
+    gemm_tc_kernel<1><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
   else
-    gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
+    gemm_tc_kernel<0><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
   return cudaGetLastError();
 }
 
