@@ -23,13 +23,14 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--hw", type=int, default=64)
+    ap.add_argument("--views", type=int, default=8, help="views per group (the 3d attention spans views*h*w tokens)")
     ap.add_argument("--ref-views", type=int, default=1,
                     help="n_ref_views promise passed with every call, as the sampler does (0 = compute every view)")
     args = ap.parse_args()
     R = args.ref_views
     dev = torch.device("cuda:0")
     unet = B200MMDMUnet.random_init(MMDM_UNET_CONFIG, seed=0, device=dev)
-    B, V, H = 2 * args.groups, 8, args.hw
+    B, V, H = 2 * args.groups, args.views, args.hw
     g = torch.Generator(device=dev).manual_seed(1)
     x = torch.randn(B, V, 4, H, H, generator=g, device=dev)
     ctrl = dict(z_input=torch.randn(B, V, 4, H, H, generator=g, device=dev),
