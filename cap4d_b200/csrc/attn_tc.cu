@@ -6,18 +6,19 @@
 // invariant to the order of the keys, so the '(n t)' interleave of the reference is not reproduced:
 // a sequence is simply the contiguous token rows [s*L, (s+1)*L) of the fused QKV matrix.
 //
-// One CTA = two 128-row Q tiles (A, B) of one (sequence, head).  384 threads:
+// One CTA = two 128-row Q tiles (A, B) of one (sequence, head).  640 threads = 5 warpgroups:
 //   WG0  warp 0 TMA producer (Q once, K/V tiles through two 4-deep rings), warps 1 / 3 MMA issuers of Q tile
-//        A / B, warp 2 TMEM owner; registers trimmed to 56/thread (setmaxnreg) and handed to the softmax warpgroups.
-//   WG1/WG2  softmax of Q tile A/B: thread <-> query row.
+//        A / B, warp 2 TMEM owner; registers trimmed to 40/thread (setmaxnreg) and handed to the softmax warpgroups.
+//   WG1-2 / WG3-4  softmax of Q tile A / B: TWO threads per query row (same TMEM lane, warps q and q + 4), each
+//        owning 64 of a tile's 128 keys and 32 of the row's 64 output columns - four softmax warps per scheduler
+//        instead of two (the two-warp version sat in fixed-latency waits with the MUFU pipe 2/3 busy).
 // Everything between the two GEMMs stays in tensor memory (512 columns: S_A S_B | O_A O_B | P_A P_B):
 //   S_X(j) = Q_X K_j^T (SS MMA, fp32)  ->  registers (S_X is released to the tensor core at once, so QK of
 //   tile j+1 overlaps the exponentials of tile j)  ->  P_X(j) = exp2(S - m) as bf16x2 back into TMEM
 //   (tcgen05.st)  ->  O_X += P_X(j) V_j (TS MMA: A operand from TMEM, V straight from its row-major TMA
 //   tile as an MN-major B operand).  O_X accumulates in TMEM over all KV tiles and is rescaled lazily
-//   (only when a row max grows by more than 2^8), so the steady-state softmax is: load S, max, 128
-//   exp2, pack, store P.  The exponentials are MUFU-bound (16/clk/SM); two warpgroups keep the MUFU
-//   busy while the other one loads / stores.
+//   (only when a row max grows by more than 2^8), so the steady-state softmax is: load S, max (exchanged
+//   between the row's two threads through shared memory), 64 exp2 per thread, pack, store P.
 #include <cstdio>
 #include <cstring>
 
@@ -37,12 +38,14 @@ constexpr int BKV = 128;  // keys per tile
 constexpr int HD = 64;    // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KiB: one Q / K / V tile
 constexpr int KS = 4, VS = 4;
-constexpr int ATTN_THREADS = 384;         // WG0: TMA / MMA / TMEM owner; WG1, WG2: softmax of Q tile A, B
+constexpr int ATTN_THREADS = 640;         // WG0: TMA / MMA / TMEM owner; WG1-2: softmax of Q tile A; WG3-4: Q tile B
+constexpr int SPLIT = 2;                  // threads per query row: each owns BKV / SPLIT keys of every tile
+constexpr int HK = BKV / SPLIT;           // keys per softmax thread and tile
 constexpr int TM_COLS = 512;
 constexpr int TM_S = 0;     // S_X (fp32 128x128)   at   0 + 128 x
 constexpr int TM_O = 256;   // O_X (fp32 128x64)    at 256 +  64 x
 constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
-constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 224;  // 128*56 + 256*224 = 64512 <= 65536
+constexpr int REGS_CTRL = 40, REGS_SOFTMAX = 104;  // pool = 640 * 96 at launch: 128 * (96 - 40) >= 512 * (104 - 96)
 constexpr float RESCALE_LOG2 = 8.0f;  // O / l are only rescaled when the row max grew by more than 2^8
 
 struct AttnBars {
@@ -54,6 +57,10 @@ struct AttnBars {
   uint64_t p_full[NQT];   // softmax -> MMA: P_X(j) is in TMEM (and O_X has been rescaled if needed)
   uint64_t pv_full[NQT];  // MMA -> softmax: O_X += P_X(j) V_j is complete
   uint32_t tmem_base;
+  // the two threads of a query row exchange their half-row maxima (double-buffered over tiles) and, at the end,
+  // their half-row sums
+  float xchg[2][NQT][SPLIT][BQ];
+  float lsum[NQT][SPLIT][BQ];
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -85,71 +92,74 @@ constexpr int TRACE_J = 16;
     if (TRACE && trace != nullptr && j < TRACE_J) trace[(static_cast<size_t>(x) * TRACE_J + j) * 8 + (slot)] = clock64(); \
   } while (0)
 
-// One KV tile of the online softmax for one query row (thread).  MASK: only the first `valid` keys count.
-// m_used is the stabiliser the running sum l and the TMEM accumulator O_X are expressed in; it only
-// follows the true row max when that grew by more than 2^RESCALE_LOG2 (P stays <= 2^8, exact in fp32/bf16
-// range), so the O rescale - a TMEM round trip - is rare after the first tiles.
+// One KV tile of the online softmax for HALF a query row: the row's 128 scores are split between two threads
+// (same TMEM lane, warps q and q + 4 of the tile's two warpgroups), which doubles the softmax warps per
+// scheduler (4 instead of 2) - ncu showed the two-warp version waiting on fixed-latency dependencies with the
+// MUFU pipe only 2/3 busy.  The halves agree on the row max through shared memory (one 64-thread named
+// barrier per tile); everything else is independent: each thread exponentiates its 64 scores, stores its 32
+// packed P columns, keeps its own partial row sum and rescales its 32 columns of O_X when the stabiliser moves.
+// MASK: only the first `valid` keys of the tile count.  m_used is the stabiliser the running sums and O_X are
+// expressed in; it only follows the true row max when that grew by more than 2^RESCALE_LOG2.
 template <bool MASK, bool TRACE>
-__device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int j, uint32_t s_addr, uint32_t o_addr,
-                                             uint32_t p_addr, float scale_log2, int valid, float& m_used,
+__device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, int r, int j, uint32_t s_addr,
+                                             uint32_t o_addr, uint32_t p_addr, float scale_log2, int valid, float& m_used,
                                              float& l_run, long long* trace) {
   ATTN_STAMP(0);
   mbar_wait(&bars->s_full[x], j & 1);
   tc_fence_after();
   ATTN_STAMP(1);
-  float s[BKV];
+  float s[HK];
   {
     uint32_t* su = reinterpret_cast<uint32_t*>(s);
     tmem_ld32(s_addr, su);
     tmem_ld32(s_addr + 32, su + 32);
-    tmem_ld32(s_addr + 64, su + 64);
-    tmem_ld32(s_addr + 96, su + 96);
     tmem_ld_wait();
   }
   tc_fence_before();
-  mbar_arrive(&bars->s_free[x]);  // the tensor core may overwrite S_X with tile j+1 now
+  mbar_arrive(&bars->s_free[x]);  // the tensor core may overwrite S_X with tile j+1 once all 256 threads arrived
   ATTN_STAMP(2);
   if (MASK) {
 #pragma unroll
-    for (int i = 0; i < BKV; ++i)
-      if (i >= valid) s[i] = -INFINITY;
+    for (int i = 0; i < HK; ++i)
+      if (half * HK + i >= valid) s[i] = -INFINITY;
   }
   float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-  for (int i = 4; i < BKV; i += 4) {
+  for (int i = 4; i < HK; i += 4) {
     mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
     mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
   }
-  const float m_new = fmaxf(m_used, fmaxf(mx0, mx1) * scale_log2);
+  const float m_half = fmaxf(mx0, mx1);
+  float* xc = &bars->xchg[j & 1][x][0][0];
+  xc[half * BQ + r] = m_half;
+  named_bar_sync(1 + x * 4 + (r >> 5), 64);  // the two warps that share these 32 rows
+  const float m_new = fmaxf(m_used, fmaxf(m_half, xc[(half ^ 1) * BQ + r]) * scale_log2);
   bool pv_waited = (j == 0);
   if (j == 0) {
     m_used = m_new;  // O_X is still empty: nothing to rescale
   } else {
     const bool grow = (m_new - m_used) > RESCALE_LOG2;
-    if (__any_sync(0xffffffffu, grow)) {
+    if (__any_sync(0xffffffffu, grow)) {  // same answer in the partner warp: it sees the same 32 row maxima
       // rare: O_X must be rescaled, which needs O_X += P_X(j-1) V_(j-1) to be complete
       mbar_wait(&bars->pv_full[x], (j - 1) & 1);
       tc_fence_after();
       pv_waited = true;
       const float f = grow ? ex2f(m_used - m_new) : 1.0f;
+      uint32_t ov[32];
+      tmem_ld32(o_addr, ov);  // this thread's 32 of the row's 64 output columns
+      tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t ov[32];
-        tmem_ld32(o_addr + h * 32, ov);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
-        tmem_st32(o_addr + h * 32, ov);
-      }
+      for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+      tmem_st32(o_addr, ov);
       l_run *= f;
       if (grow) m_used = m_new;
     }
   }
   ATTN_STAMP(3);
   float rs0 = 0.f, rs1 = 0.f;
-  uint32_t pk[BKV / 2];
+  uint32_t pk[HK / 2];
 #pragma unroll
-  for (int i = 0; i < BKV; i += 2) {
+  for (int i = 0; i < HK; i += 2) {
     const float p0 = ex2f(fmaf(s[i], scale_log2, -m_used));
     const float p1 = ex2f(fmaf(s[i + 1], scale_log2, -m_used));
     rs0 += p0;
@@ -165,7 +175,6 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int j, uint3
   }
   // P_X(j) -> TMEM as the A operand of the PV MMA: lane = query row, column c = keys (2c, 2c+1) as bf16x2
   tmem_st32(p_addr, pk);
-  tmem_st32(p_addr + 32, pk + 32);
   tmem_st_wait();
   ATTN_STAMP(5);
   tc_fence_before();
@@ -204,8 +213,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     }
     for (int i = 0; i < NQT; ++i) {
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_free[i], 128);
-      mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->s_free[i], 128 * SPLIT);
+      mbar_init(&bars->p_full[i], 128 * SPLIT);
       mbar_init(&bars->pv_full[i], 1);
     }
     fence_mbar_init();
@@ -281,49 +290,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
     }
   } else {
-    // ===================== softmax: WG1 -> Q tile 0, WG2 -> Q tile 1 =====================
+    // ===================== softmax: WG1, WG2 -> Q tile 0 (key halves 0, 1); WG3, WG4 -> Q tile 1 =====================
     setmaxnreg_inc<REGS_SOFTMAX>();
-    const int x = wg - 1;
+    const int x = (wg - 1) >> 1;
+    const int half = (wg - 1) & 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the Q tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_addr + TM_S + x * BKV;
-    const uint32_t o_addr = tmem_base + lane_addr + TM_O + x * HD;
-    const uint32_t p_addr = tmem_base + lane_addr + TM_P + x * (BKV / 2);
+    const uint32_t s_addr = tmem_base + lane_addr + TM_S + x * BKV + half * HK;
+    const uint32_t o_addr = tmem_base + lane_addr + TM_O + x * HD + half * (HD / SPLIT);
+    const uint32_t p_addr = tmem_base + lane_addr + TM_P + x * (BKV / 2) + half * (HK / 2);
     float m_used = -INFINITY, l_run = 0.f;
+    // Tile B's softmax warps start about half a tile late: the two tiles then tend to alternate on the MUFU pipe
+    // (one exponentiates while the other loads / takes its max / stores P) instead of running in lockstep.
+    // Measured -3 % on the large shapes; enforcing the alternation with named barriers costs 10 % instead.
+    if (x == 1) __nanosleep(600);
     const int valid_last = p.L - (nkv - 1) * BKV;  // valid keys in the last tile (1..128)
 
     // the key mask costs 2 ALU ops per score, so it is compiled only into the (peeled) last tile
     const bool tail = valid_last < BKV;
     const int n_main = tail ? nkv - 1 : nkv;
     long long* trace = nullptr;
-    if (TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 127) == 0) trace = p.trace;
+    if (TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 127) == 0 && half == 0)
+      trace = p.trace;
     for (int j = 0; j < n_main; ++j)
-      softmax_tile<false, TRACE>(bars, x, j, s_addr, o_addr, p_addr, p.scale_log2, BKV, m_used, l_run, trace);
+      softmax_tile<false, TRACE>(bars, x, half, r, j, s_addr, o_addr, p_addr, p.scale_log2, BKV, m_used, l_run, trace);
     if (tail)
-      softmax_tile<true, TRACE>(bars, x, nkv - 1, s_addr, o_addr, p_addr, p.scale_log2, valid_last, m_used, l_run,
-                                trace);
+      softmax_tile<true, TRACE>(bars, x, half, r, nkv - 1, s_addr, o_addr, p_addr, p.scale_log2, valid_last, m_used,
+                                l_run, trace);
+    // the row sum is the sum of the two halves' partial sums (same stabiliser in both)
+    bars->lsum[x][half][r] = l_run;
+    named_bar_sync(1 + x * 4 + q, 64);
+    const float inv = 1.0f / (l_run + bars->lsum[x][half ^ 1][r]);
     // O_X is complete once the last PV MMA has landed
     mbar_wait(&bars->pv_full[x], (nkv - 1) & 1);
     tc_fence_after();
     const int qrow = q0 + x * BQ + r;
-    const float inv = 1.0f / l_run;
-    bf16* dst = p.out + static_cast<size_t>(row_base + qrow) * p.C + head * HD;
+    bf16* dst = p.out + static_cast<size_t>(row_base + qrow) * p.C + head * HD + half * (HD / SPLIT);
+    uint32_t ov[32];
+    tmem_ld32(o_addr, ov);
+    tmem_ld_wait();
+    if (qrow < p.L) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t ov[32];
-      tmem_ld32(o_addr + h * 32, ov);
-      tmem_ld_wait();
-      if (qrow < p.L) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + h * 32 + i) = u;
-        }
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + i) = u;
       }
     }
   }
