@@ -98,6 +98,10 @@ SIGNATURES = {
                 c_void_p, c_void_p, POINTER(c_float), c_int]),
     "cap4d_b200_layernorm_bf16": (
         c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, POINTER(c_float), c_int]),
+    "cap4d_b200_cond_pos_enc": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "cap4d_b200_cond_ray_map": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cap4d_b200_last_error": (c_char_p, []),
     "cap4d_b200_version": (c_char_p, []),
 }

@@ -11,8 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcap4d_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu", "vae_exec.cu"]
+SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu", "vae_exec.cu", "cond_map.cu"]
 HEADERS = ["ptx.cuh", "kernels.h", "exec_common.h", os.path.join("..", "..", "include", "cap4d_b200.h")]
+
+# cond_map.cu decides triangle coverage with the same fp32 operations as its CPU restatement: no FMA contraction
+EXTRA_FLAGS = {"cond_map.cu": ["-fmad=false"]}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,7 +37,7 @@ def _digest() -> str:
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
     return h.hexdigest()
 
 
@@ -50,7 +53,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

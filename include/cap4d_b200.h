@@ -180,6 +180,31 @@ int cap4d_b200_vae_decode_u8(void* handle, const float* z, uint8_t* images_bgr, 
 int cap4d_b200_vae_num_launches(void* handle, int* n);
 int cap4d_b200_vae_destroy(void* handle);
 
+/* ---- conditioning maps: replaces CAP4DConditioning.forward(unconditional=False) ----------
+ * cap4d/mmdm/conditioning/cap4dcond.py:91-133 with PropRenderer.render (cap4d/mmdm/conditioning/mesh2img.py:334-379:
+ * pytorch3d 0.7.8 rasterize_meshes with cameras=None, blur_radius 0, one face per pixel, clipped barycentrics, no
+ * culling; interpolate_face_attributes), fused per view into one kernel: rasterise at (S*sr)^2 -> interpolate the
+ * template positions `props` and the expression offsets / std -> [sin(2^k p), cos(2^k p)] -> render mask -> sr x sr
+ * area average -> concat.  Channel order of pos_enc[n][S][S][C] (cap4dcond.py:104-133):
+ *   positional_channels | 3 offsets (if offsets_3d) | 3 ray map (if ray_map) | ref_mask | crop mask (if crop_mask).
+ * verts_2d / offsets_3d: [n][n_verts][3] (x, y in pytorch3d NDC, z = depth; batch["verts_2d"], batch["offsets_3d"]);
+ * faces int32 [n_faces][3], props [n_verts][3], face_mask uint8 [n_faces] = PropRenderer's buffers
+ * (mesh2img.py:348-366); ray_map [n][3][S][S], ref_mask / crop_mask [n][S][S] as the dataset provides them
+ * (cap4d/inference/data/inference_data.py:108-114).  pix_to_face (optional, int32 [n][S*sr][S*sr]) receives
+ * Fragments.pix_to_face with per-mesh face indices (-1 = background).  The unconditional branch (cap4dcond.py:78-88)
+ * is all zeros and has no entry point. */
+int cap4d_b200_cond_pos_enc(const float* verts_2d, const float* offsets_3d, const int32_t* faces, const float* props,
+                            const uint8_t* face_mask, const float* ray_map, const float* ref_mask,
+                            const float* crop_mask, float* pos_enc, int32_t* pix_to_face, int n_views, int n_verts,
+                            int n_faces, int image_size, int super_resolution, int positional_channels,
+                            float positional_multiplier, float std_expr_deformation, void* stream);
+
+/* load_camera_rays (cap4d/datasets/utils.py:161-186) followed by the rotation into the reference camera's frame
+ * (cap4d/inference/data/inference_data.py:89-100), in fp64 like the numpy original, result fp32 [n][3][S][S].
+ * cam: fp64 [n][22] on the device = new_fx, new_fy, new_cx, new_cy (utils.py:169-173), inv(extr[:3,:3]) row-major,
+ * ref_extr[:3,:3] row-major. */
+int cap4d_b200_cond_ray_map(const double* cam, float* ray_map, int n_views, int image_size, void* stream);
+
 const char* cap4d_b200_last_error(void);
 const char* cap4d_b200_version(void);
 
