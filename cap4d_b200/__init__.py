@@ -10,7 +10,9 @@ from .unet import B200MMDMUnet, config_from_reference, install  # noqa: F401
 from .sampler import B200MMLDM, B200StochasticIOSampler  # noqa: F401
 from .vae import B200VAEDecoder, install_vae  # noqa: F401
 from .conditioning import B200CAP4DConditioning, install_conditioning  # noqa: F401
+from .output import convert_and_save_latent_images, save_flame_params, save_visualization  # noqa: F401
 
 __all__ = ["B200MMDMUnet", "B200MMLDM", "B200StochasticIOSampler", "B200VAEDecoder", "install_vae", "B200CAP4DConditioning",
-           "install_conditioning", "MMDMSchedule", "ddim_factors",
+           "install_conditioning", "convert_and_save_latent_images", "save_flame_params", "save_visualization",
+           "MMDMSchedule", "ddim_factors",
            "ddim_timesteps", "config_from_reference", "install"]

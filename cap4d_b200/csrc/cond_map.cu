@@ -28,7 +28,7 @@ namespace {
 
 constexpr float kEpsilon = 1e-8f;  // pytorch3d rasterization_utils.cuh
 constexpr int TILE = 8;            // output pixels per tile side
-constexpr int LIST_CAP = 1024;     // faces culled per pass (bounds the shared-memory list)
+constexpr int LIST_CAP = 768;      // faces culled per pass (bounds the shared-memory list)
 
 struct FaceRec {  // one culled face: its three vertices (NDC x, y; depth z) and its index
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
@@ -60,6 +60,7 @@ __device__ __forceinline__ float pix_to_ndc(int i, int S) { return -1.0f + (2.0f
 
 __global__ void __launch_bounds__(TILE* TILE * 16) cond_pos_enc_kernel(CondParams p) {
   __shared__ __align__(16) unsigned char smem_raw[LIST_CAP * sizeof(FaceRec)];
+  __shared__ float4 list_bbox[LIST_CAP];  // xmin, xmax, ymin, ymax of the culled faces: all a rejected sample reads
   __shared__ int list_n;
   FaceRec* list = reinterpret_cast<FaceRec*>(smem_raw);
   float* tile_out = reinterpret_cast<float*>(smem_raw);  // reused after the face loop: [TILE*TILE][Ctot]
@@ -106,16 +107,19 @@ __global__ void __launch_bounds__(TILE* TILE * 16) cond_pos_enc_kernel(CondParam
       const bool zero_area = (area <= kEpsilon && area >= -kEpsilon);
       const bool z_invalid = zmin < kEpsilon;
       const bool off_tile = (t_xlo > xmax || t_xhi < xmin || t_ylo > ymax || t_yhi < ymin);
-      if (!(zero_area || z_invalid || off_tile)) list[atomicAdd(&list_n, 1)] = r;
+      if (!(zero_area || z_invalid || off_tile)) {
+        const int at = atomicAdd(&list_n, 1);
+        list[at] = r;
+        list_bbox[at] = make_float4(xmin, xmax, ymin, ymax);
+      }
     }
     __syncthreads();
     const int ln = list_n;
     if (in_img) {
       for (int j = 0; j < ln; ++j) {
-        const FaceRec r = list[j];  // broadcast reads
-        const float xmin = fminf(r.x0, fminf(r.x1, r.x2)), xmax = fmaxf(r.x0, fmaxf(r.x1, r.x2));
-        const float ymin = fminf(r.y0, fminf(r.y1, r.y2)), ymax = fmaxf(r.y0, fmaxf(r.y1, r.y2));
-        if (px > xmax || px < xmin || py > ymax || py < ymin) continue;
+        const float4 bb = list_bbox[j];  // broadcast read
+        if (px > bb.y || px < bb.x || py > bb.w || py < bb.z) continue;
+        const FaceRec r = list[j];
         // BarycentricCoordsForward
         const float area = edge_fn(r.x2, r.y2, r.x0, r.y0, r.x1, r.y1) + kEpsilon;
         const float w0 = edge_fn(px, py, r.x1, r.y1, r.x2, r.y2) / area;
@@ -161,11 +165,11 @@ __global__ void __launch_bounds__(TILE* TILE * 16) cond_pos_enc_kernel(CondParam
   // them in raster order (the order of adaptive_avg_pool2d), lane `sub == 0` keeps the result
   const unsigned lane = tid & 31u;
   const unsigned base = lane - sub;
-  const float cnt = static_cast<float>(sr2);
+  const float inv_cnt = 1.0f / static_cast<float>(sr2);  // sr2 is 1, 4 or 16: multiplying is exact division
   auto pool = [&](float v) {
     float s = 0.f;
     for (int j = 0; j < sr2; ++j) s += __shfl_sync(0xffffffffu, v, base + j);
-    return s / cnt;
+    return s * inv_cnt;
   };
   float* my_out = tile_out + pix * p.Ctot;
   const int nf = p.n_freq;
@@ -174,7 +178,12 @@ __global__ void __launch_bounds__(TILE* TILE * 16) cond_pos_enc_kernel(CondParam
     float freq = 1.0f;
     for (int k = 0; k < nf; ++k) {
       const float a = v * freq;
-      const float s = pool(sinf(a) * mask), co = pool(cosf(a) * mask);
+      float sv = 0.f, cv = 0.f;
+      if (mask != 0.f) {  // two thirds of the samples are background or masked: their contribution is 0
+        sv = sinf(a);
+        cv = cosf(a);
+      }
+      const float s = pool(sv), co = pool(cv);
       if (sub == 0) {
         my_out[c * 2 * nf + k] = s;
         my_out[c * 2 * nf + nf + k] = co;
@@ -201,13 +210,20 @@ __global__ void __launch_bounds__(TILE* TILE * 16) cond_pos_enc_kernel(CondParam
     if (p.crop_mask != nullptr) my_out[ch++] = __ldg(p.crop_mask + static_cast<size_t>(view) * plane + at);
   }
   __syncthreads();
-  // coalesced write of the tile: each tile row is TILE * Ctot consecutive floats of the output
+  // coalesced write of the tile: each tile row is (valid columns) * Ctot consecutive floats of the output
   const int row_len = TILE * p.Ctot;
-  for (int idx = tid; idx < TILE * row_len; idx += nthr) {
-    const int ry = idx / row_len, rem = idx % row_len;
-    const int gy = tile_y * TILE + ry, gx = tile_x * TILE + rem / p.Ctot;
-    if (gy < p.S && gx < p.S)
-      p.out[((static_cast<size_t>(view) * p.S + gy) * p.S + tile_x * TILE) * p.Ctot + rem] = tile_out[ry * row_len + rem];
+  const int valid = min(TILE, p.S - tile_x * TILE) * p.Ctot;
+  const int rows = min(TILE, p.S - tile_y * TILE);
+  const bool vec = (valid == row_len) && ((p.S * p.Ctot) % 4 == 0);  // rows start on 16-byte boundaries
+  for (int ry = 0; ry < rows; ++ry) {
+    float* dst = p.out + ((static_cast<size_t>(view) * p.S + tile_y * TILE + ry) * p.S + tile_x * TILE) * p.Ctot;
+    const float* src = tile_out + ry * row_len;
+    if (vec) {
+      for (int e = tid; e < row_len / 4; e += nthr)
+        reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+    } else {
+      for (int e = tid; e < valid; e += nthr) dst[e] = src[e];
+    }
   }
 }
 
@@ -249,6 +265,7 @@ int cap4d_b200_cond_pos_enc(const float* verts_2d, const float* offsets_3d, cons
                             const float* crop_mask, float* pos_enc, int32_t* pix_to_face, int n_views, int n_verts,
                             int n_faces, int image_size, int super_resolution, int positional_channels,
                             float positional_multiplier, float std_expr_deformation, void* stream) {
+  if (n_views == 0) return 0;  // an empty batch has nothing to read or write
   if (verts_2d == nullptr || faces == nullptr || props == nullptr || face_mask == nullptr || ref_mask == nullptr ||
       pos_enc == nullptr) {
     set_error("cond_pos_enc: verts_2d, faces, props, face_mask, ref_mask and pos_enc are required");
@@ -267,7 +284,6 @@ int cap4d_b200_cond_pos_enc(const float* verts_2d, const float* offsets_3d, cons
     set_error("cond_pos_enc: positional_channels must be a positive multiple of 6");
     return 20;
   }
-  if (n_views == 0) return 0;
   CondParams p;
   p.verts = verts_2d; p.offsets = offsets_3d; p.faces = faces; p.props = props; p.fmask = face_mask;
   p.ray_map = ray_map; p.ref_mask = ref_mask; p.crop_mask = crop_mask; p.out = pos_enc; p.pix_to_face = pix_to_face;

@@ -102,3 +102,16 @@ def test_vae_production_config(cuda_device):
     err, p = O.max_rel_err(y.cpu(), ref.cpu()), O.psnr(y.cpu(), ref.cpu())
     print(f"production VAE decode 2 x 512x512: max-rel {err:.3e} PSNR {p:.1f} dB, {vae.num_launches()} launches")
     assert y.shape == (2, 3, 512, 512) and err < TOL and p >= 40.0
+
+
+def test_convert_and_save_latent_images_end_to_end(cuda_device, tiny_vaes, tmp_path):
+    """latents -> images/%05d.png through the reference-named writer; the files hold exactly the
+    uint8 arrays of decode_to_uint8_bgr (batched decode, threaded encode) in latent order."""
+    from cap4d_b200 import output as OUT
+
+    vae, _ = tiny_vaes(0)
+    z = torch.randn(5, 4, 8, 8, generator=torch.Generator().manual_seed(21)) * 0.8
+    want = vae.decode_to_uint8_bgr(z, batch=2).numpy()
+    assert OUT.convert_and_save_latent_images(z, vae, cuda_device, tmp_path, batch=2, writers=2) == 5
+    assert sorted(os.listdir(tmp_path / "images")) == [f"{i:05d}.png" for i in range(5)]
+    assert np.array_equal(OUT.read_output_images(tmp_path)[..., ::-1], want)
