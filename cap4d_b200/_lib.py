@@ -100,7 +100,8 @@ SIGNATURES = {
         c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, POINTER(c_float), c_int]),
     "cap4d_b200_cond_pos_enc": (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+                c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "cap4d_b200_cond_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "cap4d_b200_cond_ray_map": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cap4d_b200_last_error": (c_char_p, []),
     "cap4d_b200_version": (c_char_p, []),

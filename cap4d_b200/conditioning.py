@@ -72,6 +72,7 @@ class B200CAP4DConditioning(torch.nn.Module):
         self.register_buffer("faces", faces.detach().to(torch.int32).contiguous())
         self.register_buffer("props", props.detach().to(torch.float32).contiguous())
         self.register_buffer("face_mask", face_mask.detach().to(torch.uint8).contiguous())
+        self._ws = None  # per-face tile ranges of the kernel's pre-pass (grown on demand)
         if self.faces.dim() != 2 or self.faces.shape[1] != 3 or self.props.shape[1] != 3:
             raise ValueError("faces must be [F,3] and props [Nv,3]")
         if int(self.faces.min()) < 0 or int(self.faces.max()) >= self.props.shape[0]:
@@ -161,12 +162,20 @@ class B200CAP4DConditioning(torch.nn.Module):
         out = torch.empty((n, S, S, C), device=dev, dtype=torch.float32)
         p2f = torch.empty((n, S * sr, S * sr), device=dev, dtype=torch.int32) if return_pix_to_face else None
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()  # noqa: E731
+        if n == 0:
+            return (out, p2f) if return_pix_to_face else out
+        nbytes = ctypes.c_size_t()
+        _lib.check(_lib.load().cap4d_b200_cond_workspace_bytes(n, self.faces.shape[0], ctypes.byref(nbytes)),
+                   "cond_workspace_bytes")
+        ws = self._ws
+        if ws is None or ws.device != dev or ws.numel() < nbytes.value:
+            ws = self._ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().cap4d_b200_cond_pos_enc(
                 ptr(verts_2d), ptr(offsets_3d), ptr(self.faces), ptr(self.props), ptr(self.face_mask), ptr(ray_map),
                 ptr(ref_mask), ptr(crop_mask), ptr(out), ptr(p2f), n, nv, self.faces.shape[0], S, sr,
                 self.positional_channels, float(self.positional_multiplier), float(self.std_expr_deformation),
-                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "cond_pos_enc")
+                ptr(ws), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "cond_pos_enc")
         return (out, p2f) if return_pix_to_face else out
 
 

@@ -191,13 +191,16 @@ int cap4d_b200_vae_destroy(void* handle);
  * faces int32 [n_faces][3], props [n_verts][3], face_mask uint8 [n_faces] = PropRenderer's buffers
  * (mesh2img.py:348-366); ray_map [n][3][S][S], ref_mask / crop_mask [n][S][S] as the dataset provides them
  * (cap4d/inference/data/inference_data.py:108-114).  pix_to_face (optional, int32 [n][S*sr][S*sr]) receives
- * Fragments.pix_to_face with per-mesh face indices (-1 = background).  The unconditional branch (cap4dcond.py:78-88)
- * is all zeros and has no entry point. */
+ * Fragments.pix_to_face with per-mesh face indices (-1 = background).  workspace: caller-owned device scratch of
+ * cap4d_b200_cond_workspace_bytes(n_views, n_faces) bytes (the per-face tile ranges of the pre-pass).  The
+ * unconditional branch (cap4dcond.py:78-88) is all zeros and has no entry point. */
+int cap4d_b200_cond_workspace_bytes(int n_views, int n_faces, size_t* bytes);
 int cap4d_b200_cond_pos_enc(const float* verts_2d, const float* offsets_3d, const int32_t* faces, const float* props,
                             const uint8_t* face_mask, const float* ray_map, const float* ref_mask,
                             const float* crop_mask, float* pos_enc, int32_t* pix_to_face, int n_views, int n_verts,
                             int n_faces, int image_size, int super_resolution, int positional_channels,
-                            float positional_multiplier, float std_expr_deformation, void* stream);
+                            float positional_multiplier, float std_expr_deformation, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* load_camera_rays (cap4d/datasets/utils.py:161-186) followed by the rotation into the reference camera's frame
  * (cap4d/inference/data/inference_data.py:89-100), in fp64 like the numpy original, result fp32 [n][3][S][S].

@@ -85,7 +85,7 @@ def main():
                      "note": "the face walk (compare/FMUL work per sample), not the 1 MB/view of traffic, bounds it"},
         "e2e": {"value": n / e2e_s, "unit": "views/s", "h2d_bytes": int(sum(x.numel() * x.element_size() for x in host)),
                 "d2h_bytes": int(out_host.numel() * 4)},
-        "gpu_launches": 1,
+        "gpu_launches": 2,
     }
     if not args.no_cpu:
         t0 = time.perf_counter()

@@ -167,13 +167,18 @@ def test_c_abi_rejects_bad_arguments_without_gpu():
 
     lib = _lib.load()
     one = (np.zeros(16, np.float32)).ctypes.data
-    args = lambda sr, pc, n_faces: (one, None, one, one, one, None, one, None, one, None, 1, 3, n_faces, 8, sr, pc,  # noqa: E731
-                                    1.0, 0.0104, None)
+    args = lambda sr, pc, n_faces, ws=one, nb=64: (one, None, one, one, one, None, one, None, one, None, 1, 3,  # noqa: E731
+                                                   n_faces, 8, sr, pc, 1.0, 0.0104, ws, nb, None)
     assert lib.cap4d_b200_cond_pos_enc(*args(3, 42, 1)) != 0 and "super_resolution" in _lib.last_error()
     assert lib.cap4d_b200_cond_pos_enc(*args(2, 40, 1)) != 0 and "positional_channels" in _lib.last_error()
     assert lib.cap4d_b200_cond_pos_enc(*args(2, 42, 0)) != 0
     assert lib.cap4d_b200_cond_pos_enc(None, None, one, one, one, None, one, None, one, None, 1, 3, 1, 8, 2, 42, 1.0,
-                                       0.0104, None) != 0
+                                       0.0104, one, 64, None) != 0
+    assert lib.cap4d_b200_cond_pos_enc(*args(2, 42, 4, nb=8)) != 0 and "workspace" in _lib.last_error()
+    import ctypes
+    nbytes = ctypes.c_size_t()
+    assert lib.cap4d_b200_cond_workspace_bytes(840, 10316, ctypes.byref(nbytes)) == 0 and nbytes.value == 840 * 10316 * 4
+    assert lib.cap4d_b200_cond_workspace_bytes(3, 10, ctypes.byref(nbytes)) == 0 and nbytes.value == 3 * 10 * 4
     assert lib.cap4d_b200_cond_ray_map(None, one, 1, 8, None) != 0
 
 
