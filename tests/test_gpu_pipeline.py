@@ -62,7 +62,7 @@ def test_conditioning_sampler_decode_files(cuda_device, tmp_path):
     torch.manual_seed(7)
     np.random.seed(7)
     z = B200StochasticIOSampler(B200MMLDM(unet), groups_per_call=2).sample(
-        S=3, ref_cond=ref_c, ref_uncond=ref_u, gen_cond=gen_c, gen_uncond=gen_u, latent_shape=(4, S, S), V=4, R_max=4,
+        S=4, ref_cond=ref_c, ref_uncond=ref_u, gen_cond=gen_c, gen_uncond=gen_u, latent_shape=(4, S, S), V=4, R_max=4,
         cfg_scale=2.0)
     assert z.shape == (n_gen, 4, S, S)
     pe = torch.from_numpy(want_pe)
@@ -73,7 +73,7 @@ def test_conditioning_sampler_decode_files(cuda_device, tmp_path):
     acp = O.mmdm_schedule()[1].astype(np.float32)
     torch.manual_seed(7)
     np.random.seed(7)
-    z_want = O.stochastic_io_sample(lambda a, b, c: O.unet_forward(sd, cfg, a, b, c), acp, 3, o_ref_c, zero(o_ref_c),
+    z_want = O.stochastic_io_sample(lambda a, b, c: O.unet_forward(sd, cfg, a, b, c), acp, 4, o_ref_c, zero(o_ref_c),
                                     o_gen_c, zero(o_gen_c), (4, S, S), V=4, R_max=4, cfg_scale=2.0)
     assert O.psnr(z.cpu(), z_want) >= 40.0
 
