@@ -62,6 +62,9 @@ SIGNATURES = {
     "cap4d_b200_vae_decode_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p,
                                          c_size_t, c_void_p]),
     "cap4d_b200_vae_num_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_vae_has_encoder": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_vae_encode_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "cap4d_b200_vae_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cap4d_b200_vae_destroy": (c_int, [c_void_p]),
     "cap4d_b200_unet_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "cap4d_b200_unet_forward": (

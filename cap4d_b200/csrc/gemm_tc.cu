@@ -942,10 +942,6 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
     set_error("conv: output H and W must be powers of two");
     return false;
   }
-  if (W > BM && g.stride != 1) {
-    set_error("conv: stride 2 needs W <= 128");
-    return false;
-  }
   if (Cin % BK != 0 || (A2 != nullptr && K2 % BK != 0)) {
     set_error("conv: Cin must be a multiple of 64");
     return false;
@@ -987,11 +983,20 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
         p.tap_dy[t] = ky - 1;
         p.tap_dn[t] = 0;
       } else {
-        // input pixel (2*oy + ky - 1, 2*ox + kx - 1): parity plane ((ky-1)&1, (kx-1)&1), shifted by -1 for ky/kx == 0
-        const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // ky=0 -> odd, 1 -> even, 2 -> odd
-        p.tap_dy[t] = (ky == 0) ? -1 : 0;
-        p.tap_dx[t] = (kx == 0) ? -1 : 0;
-        p.tap_dn[t] = (py * 2 + px) * g.n_img;
+        if (g.asym_pad) {
+          // input pixel (2*oy + ky, 2*ox + kx): parity plane (ky&1, kx&1), shifted by +1 for ky/kx == 2; the zero
+          // row/column F.pad adds below / right of the image is the TMA out-of-bounds fill
+          const int py = ky & 1, px = kx & 1;
+          p.tap_dy[t] = ky >> 1;
+          p.tap_dx[t] = kx >> 1;
+          p.tap_dn[t] = (py * 2 + px) * g.n_img;
+        } else {
+          // input pixel (2*oy + ky - 1, 2*ox + kx - 1): parity plane ((ky-1)&1, (kx-1)&1), shifted by -1 for ky/kx == 0
+          const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // ky=0 -> odd, 1 -> even, 2 -> odd
+          p.tap_dy[t] = (ky == 0) ? -1 : 0;
+          p.tap_dx[t] = (kx == 0) ? -1 : 0;
+          p.tap_dn[t] = (py * 2 + px) * g.n_img;
+        }
         planes = 4;
       }
     }

@@ -73,6 +73,9 @@ struct ConvGeom {
   // folded into a 2x2-tap conv on the LOW-resolution grid H x W; taps = 4, weights [Cout][4*Cin] are the
   // phase-summed 3x3 taps, and output row (n, y, x) is written to pixel (n, 2y+py, 2x+px) of the 2H x 2W map
   int up_phase = -1;
+  // stride 2 only: 0 = Conv2d(k 3, stride 2, padding 1) (openaimodel.py Downsample); 1 = the VAE encoder's
+  // F.pad(x, (0,1,0,1)) + Conv2d(k 3, stride 2, padding 0) (model.py:80-84): taps reach rows/cols 2y .. 2y+2
+  int asym_pad = 0;
 };
 
 // Plain GEMM: A [M][K] bf16 (lda == K), optional second segment A2 [M][K2].

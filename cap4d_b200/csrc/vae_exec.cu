@@ -40,7 +40,7 @@ struct VConv {
   bf16* w = nullptr;
   float* b = nullptr;
 };
-enum VKind { V_RES, V_ATTN, V_UP };
+enum VKind { V_RES, V_ATTN, V_UP, V_DOWN };
 struct VLayer {
   VKind kind;
   int idx;
@@ -59,6 +59,21 @@ struct Vae {
   bf16* w_in = nullptr;
   float *b_in = nullptr, *w_pq = nullptr, *b_pq = nullptr, *out_gn_g = nullptr, *out_gn_b = nullptr, *b_out = nullptr;
   bf16* w_out = nullptr;
+  // encoder (model.py:452-545 + quant_conv, autoencoder.py:82-85); optional: built when its weights were loaded
+  std::vector<VRes> eres;
+  std::vector<VAttn> eattn;
+  std::vector<VConv> down;
+  std::vector<VLayer> elayers;
+  bool has_encoder = false;
+  int e_c_last = 0;
+  bf16 *ew_in = nullptr, *ew_out = nullptr;
+  float *eb_in = nullptr, *eb_out = nullptr, *e_gn_g = nullptr, *e_gn_b = nullptr, *e_ident = nullptr, *e_zero = nullptr;
+  std::vector<Op> eops;
+  const float* io_img = nullptr;
+  float* io_moments = nullptr;
+  int eN = 0, eH = 0, eW = 0;
+  void* e_ws = nullptr;
+  size_t e_ws_bytes = 0;
   // plan
   std::vector<Op> ops;
   const float* io_z = nullptr;
@@ -126,7 +141,84 @@ struct Vae {
         set_error("vae: ResnetBlock channels must be multiples of 64 (in) / 32 (out) for the conv kernel");
         return false;
       }
+    // Encoder.__init__ (model.py:466-516): attn_resolutions = [] : mid-block attention only
+    int eb = cfg.ch;
+    auto add_eres = [&](const std::string& p, int cin, int cout) {
+      VRes r;
+      r.prefix = p;
+      r.cin = cin;
+      r.cout = cout;
+      r.skip = cin != cout;
+      eres.push_back(r);
+      elayers.push_back({V_RES, static_cast<int>(eres.size()) - 1});
+    };
+    for (int lvl = 0; lvl < cfg.n_levels; ++lvl) {
+      const int block_out = cfg.ch * cfg.ch_mult[lvl];
+      for (int i = 0; i < cfg.num_res_blocks; ++i) {
+        add_eres("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(i) + ".", eb, block_out);
+        eb = block_out;
+      }
+      if (lvl != cfg.n_levels - 1) {
+        VConv d;
+        d.prefix = "encoder.down." + std::to_string(lvl) + ".downsample.conv.";
+        d.cin = d.cout = eb;
+        down.push_back(d);
+        elayers.push_back({V_DOWN, static_cast<int>(down.size()) - 1});
+      }
+    }
+    add_eres("encoder.mid.block_1.", eb, eb);
+    {
+      VAttn a;
+      a.prefix = "encoder.mid.attn_1.";
+      a.C = eb;
+      eattn.push_back(a);
+      elayers.push_back({V_ATTN, 0});
+    }
+    add_eres("encoder.mid.block_2.", eb, eb);
+    e_c_last = eb;
     return true;
+  }
+
+  // parameters of the encoder half (same naming as the reference's state_dict); optional as a whole
+  std::vector<std::pair<std::string, std::vector<int64_t>>> expected_encoder_params() const {
+    std::vector<std::pair<std::string, std::vector<int64_t>>> v;
+    auto add = [&](const std::string& n, std::vector<int64_t> s) { v.emplace_back(n, std::move(s)); };
+    const int z2 = 2 * cfg.z_channels, e2 = 2 * cfg.embed_dim;
+    add("encoder.conv_in.weight", {cfg.ch, cfg.out_ch, 3, 3});
+    add("encoder.conv_in.bias", {cfg.ch});
+    for (const VRes& r : eres) {
+      add(r.prefix + "norm1.weight", {r.cin});
+      add(r.prefix + "norm1.bias", {r.cin});
+      add(r.prefix + "conv1.weight", {r.cout, r.cin, 3, 3});
+      add(r.prefix + "conv1.bias", {r.cout});
+      add(r.prefix + "norm2.weight", {r.cout});
+      add(r.prefix + "norm2.bias", {r.cout});
+      add(r.prefix + "conv2.weight", {r.cout, r.cout, 3, 3});
+      add(r.prefix + "conv2.bias", {r.cout});
+      if (r.skip) {
+        add(r.prefix + "nin_shortcut.weight", {r.cout, r.cin, 1, 1});
+        add(r.prefix + "nin_shortcut.bias", {r.cout});
+      }
+    }
+    for (const VAttn& a : eattn) {
+      add(a.prefix + "norm.weight", {a.C});
+      add(a.prefix + "norm.bias", {a.C});
+      for (const char* n : {"q", "k", "v", "proj_out"}) {
+        add(a.prefix + n + ".weight", {a.C, a.C, 1, 1});
+        add(a.prefix + n + ".bias", {a.C});
+      }
+    }
+    for (const VConv& d : down) {
+      add(d.prefix + "weight", {d.cout, d.cin, 3, 3});
+      add(d.prefix + "bias", {d.cout});
+    }
+    add("encoder.norm_out.weight", {e_c_last});
+    add("encoder.norm_out.bias", {e_c_last});
+    add("encoder.conv_out.weight", {z2, e_c_last, 3, 3});
+    add("encoder.conv_out.bias", {z2});
+    add("quant_conv.weight", {e2, z2, 1, 1});
+    add("quant_conv.bias", {e2});
+    return v;
   }
 
   std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params() const {
@@ -206,6 +298,60 @@ struct Vae {
     return true;
   }
 
+  // ResnetBlock / AttnBlock weights -> kernel layouts (shared by the decoder and the encoder)
+  bool finalize_res(VRes& r) {
+    const RawTensor* t;
+    const std::string& p = r.prefix;
+    if (!fp(p + "norm1.weight", r.cin, &r.gn1_g) || !fp(p + "norm1.bias", r.cin, &r.gn1_b) ||
+        !fp(p + "norm2.weight", r.cout, &r.gn2_g) || !fp(p + "norm2.bias", r.cout, &r.gn2_b) ||
+        !fp(p + "conv1.bias", r.cout, &r.b1))
+      return false;
+    r.w1 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * 9 * r.cin);
+    const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
+    r.w2 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * k2);
+    r.b2 = dev_alloc<float>(r.cout);
+    if (!r.w1 || !r.w2 || !r.b2) {
+      set_error("cudaMalloc failed");
+      return false;
+    }
+    if (!pack_conv(p + "conv1.weight", r.cout, r.cin, r.w1, 9 * r.cin)) return false;
+    if (!pack_conv(p + "conv2.weight", r.cout, r.cout, r.w2, k2)) return false;
+    float *bo, *bs = nullptr;
+    if (!fp(p + "conv2.bias", r.cout, &bo)) return false;
+    if (r.skip) {  // nin_shortcut (model.py:113-123) appended along K of conv2
+      if (!get(p + "nin_shortcut.weight", static_cast<size_t>(r.cout) * r.cin, &t)) return false;
+      CUDA_OK(launch_pack_matrix(t->d, r.cout, r.cin, r.w2, k2, 9 * r.cout, 0, 0));
+      if (!fp(p + "nin_shortcut.bias", r.cout, &bs)) return false;
+    }
+    vec_add_kernel<<<(r.cout + 255) / 256, 256>>>(bo, bs, r.b2, r.cout);
+    return true;
+  }
+
+  bool finalize_attn(VAttn& a) {
+    const RawTensor* t;
+    const int C = a.C;
+    if (!fp(a.prefix + "norm.weight", C, &a.gn_g) || !fp(a.prefix + "norm.bias", C, &a.gn_b) ||
+        !fp(a.prefix + "proj_out.bias", C, &a.bo))
+      return false;
+    a.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
+    a.bqkv = dev_alloc<float>(static_cast<size_t>(3) * C);
+    a.wo = dev_alloc<bf16>(static_cast<size_t>(C) * C);
+    if (!a.wqkv || !a.bqkv || !a.wo) {
+      set_error("cudaMalloc failed");
+      return false;
+    }
+    const char* names[3] = {"q", "k", "v"};
+    for (int i = 0; i < 3; ++i) {  // 1x1 convs == linears: rows [i*C, (i+1)*C) of the fused [3C][C] matrix
+      if (!get(a.prefix + names[i] + ".weight", static_cast<size_t>(C) * C, &t)) return false;
+      CUDA_OK(launch_pack_matrix(t->d, C, C, a.wqkv, C, 0, i * C, 0));
+      if (!get(a.prefix + names[i] + ".bias", C, &t)) return false;
+      CUDA_OK(cudaMemcpy(a.bqkv + static_cast<size_t>(i) * C, t->d, C * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    if (!get(a.prefix + "proj_out.weight", static_cast<size_t>(C) * C, &t)) return false;
+    CUDA_OK(launch_pack_matrix(t->d, C, C, a.wo, C, 0, 0, 0));
+    return true;
+  }
+
   bool finalize() {
     if (finalized) return true;
     for (const auto& kv : expected_params()) {
@@ -226,53 +372,10 @@ struct Vae {
     // conv_in over im2col rows [tap*zc + c], K padded to 64 (vae_input_pack_kernel)
     w_in = dev_alloc<bf16>(static_cast<size_t>(c_in) * kpad_in, true);
     if (!w_in || !pack_conv("decoder.conv_in.weight", c_in, zc, w_in, kpad_in)) return false;
-    for (VRes& r : res) {
-      const std::string& p = r.prefix;
-      if (!fp(p + "norm1.weight", r.cin, &r.gn1_g) || !fp(p + "norm1.bias", r.cin, &r.gn1_b) ||
-          !fp(p + "norm2.weight", r.cout, &r.gn2_g) || !fp(p + "norm2.bias", r.cout, &r.gn2_b) ||
-          !fp(p + "conv1.bias", r.cout, &r.b1))
-        return false;
-      r.w1 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * 9 * r.cin);
-      const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
-      r.w2 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * k2);
-      r.b2 = dev_alloc<float>(r.cout);
-      if (!r.w1 || !r.w2 || !r.b2) {
-        set_error("cudaMalloc failed");
-        return false;
-      }
-      if (!pack_conv(p + "conv1.weight", r.cout, r.cin, r.w1, 9 * r.cin)) return false;
-      if (!pack_conv(p + "conv2.weight", r.cout, r.cout, r.w2, k2)) return false;
-      float *bo, *bs = nullptr;
-      if (!fp(p + "conv2.bias", r.cout, &bo)) return false;
-      if (r.skip) {  // nin_shortcut (model.py:113-123) appended along K of conv2
-        if (!get(p + "nin_shortcut.weight", static_cast<size_t>(r.cout) * r.cin, &t)) return false;
-        CUDA_OK(launch_pack_matrix(t->d, r.cout, r.cin, r.w2, k2, 9 * r.cout, 0, 0));
-        if (!fp(p + "nin_shortcut.bias", r.cout, &bs)) return false;
-      }
-      vec_add_kernel<<<(r.cout + 255) / 256, 256>>>(bo, bs, r.b2, r.cout);
-    }
-    for (VAttn& a : attn) {
-      const int C = a.C;
-      if (!fp(a.prefix + "norm.weight", C, &a.gn_g) || !fp(a.prefix + "norm.bias", C, &a.gn_b) ||
-          !fp(a.prefix + "proj_out.bias", C, &a.bo))
-        return false;
-      a.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
-      a.bqkv = dev_alloc<float>(static_cast<size_t>(3) * C);
-      a.wo = dev_alloc<bf16>(static_cast<size_t>(C) * C);
-      if (!a.wqkv || !a.bqkv || !a.wo) {
-        set_error("cudaMalloc failed");
-        return false;
-      }
-      const char* names[3] = {"q", "k", "v"};
-      for (int i = 0; i < 3; ++i) {  // 1x1 convs == linears: rows [i*C, (i+1)*C) of the fused [3C][C] matrix
-        if (!get(a.prefix + names[i] + ".weight", static_cast<size_t>(C) * C, &t)) return false;
-        CUDA_OK(launch_pack_matrix(t->d, C, C, a.wqkv, C, 0, i * C, 0));
-        if (!get(a.prefix + names[i] + ".bias", C, &t)) return false;
-        CUDA_OK(cudaMemcpy(a.bqkv + static_cast<size_t>(i) * C, t->d, C * sizeof(float), cudaMemcpyDeviceToDevice));
-      }
-      if (!get(a.prefix + "proj_out.weight", static_cast<size_t>(C) * C, &t)) return false;
-      CUDA_OK(launch_pack_matrix(t->d, C, C, a.wo, C, 0, 0, 0));
-    }
+    for (VRes& r : res)
+      if (!finalize_res(r)) return false;
+    for (VAttn& a : attn)
+      if (!finalize_attn(a)) return false;
     for (VConv& u : up) {
       u.w = dev_alloc<bf16>(static_cast<size_t>(16) * u.cout * u.cin);  // 4 phases x [cout][4*cin]
       if (!u.w || !get(u.prefix + "weight", static_cast<size_t>(u.cout) * u.cin * 9, &t)) return false;
@@ -285,8 +388,80 @@ struct Vae {
     if (!w_out || !b_out || !pack_conv("decoder.conv_out.weight", cfg.out_ch, c_last, w_out, 9 * c_last)) return false;
     if (!get("decoder.conv_out.bias", cfg.out_ch, &t)) return false;
     CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_ch * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (raw.count("encoder.conv_in.weight") && !finalize_encoder()) return false;
     CUDA_OK(cudaDeviceSynchronize());
     finalized = true;
+    return true;
+  }
+
+  // Encoder weights (model.py:466-516) + quant_conv (autoencoder.py:84), folded into conv_out: the 1x1 conv
+  // is a [2e][2z] matrix applied to conv_out's outputs, so W' = Wq Wc and b' = Wq bc + bq (computed in fp32 here).
+  bool finalize_encoder() {
+    for (const auto& kv : expected_encoder_params()) {
+      size_t n = 1;
+      for (int64_t d : kv.second) n *= static_cast<size_t>(d);
+      const RawTensor* t;
+      if (!get(kv.first, n, &t)) return false;
+    }
+    const int cin_img = cfg.out_ch, z2 = 2 * cfg.z_channels, e2 = 2 * cfg.embed_dim;
+    if (9 * cin_img > kpad_in || e2 > 32) {
+      set_error("vae encoder: 9 * image channels must fit 64 and 2 * embed_dim 32");
+      return false;
+    }
+    if (!fp("encoder.conv_in.bias", cfg.ch, &eb_in)) return false;
+    ew_in = dev_alloc<bf16>(static_cast<size_t>(cfg.ch) * kpad_in, true);
+    if (!ew_in || !pack_conv("encoder.conv_in.weight", cfg.ch, cin_img, ew_in, kpad_in)) return false;
+    // the image goes through the latent im2col pack kernel with an identity "post_quant_conv"
+    e_ident = dev_alloc<float>(static_cast<size_t>(cin_img) * cin_img, true);
+    e_zero = dev_alloc<float>(cin_img, true);
+    if (!e_ident || !e_zero) return false;
+    {
+      std::vector<float> eye(static_cast<size_t>(cin_img) * cin_img, 0.f);
+      for (int i = 0; i < cin_img; ++i) eye[static_cast<size_t>(i) * cin_img + i] = 1.f;
+      CUDA_OK(cudaMemcpy(e_ident, eye.data(), eye.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    for (VRes& r : eres) {
+      if (r.cin % 64 != 0 || r.cout % 32 != 0) {
+        set_error("vae encoder: ResnetBlock channels must be multiples of 64 (in) / 32 (out) for the conv kernel");
+        return false;
+      }
+      if (!finalize_res(r)) return false;
+    }
+    for (VAttn& a : eattn)
+      if (!finalize_attn(a)) return false;
+    for (VConv& d : down) {
+      d.w = dev_alloc<bf16>(static_cast<size_t>(d.cout) * 9 * d.cin);
+      if (!d.w || !pack_conv(d.prefix + "weight", d.cout, d.cin, d.w, 9 * d.cin)) return false;
+      if (!fp(d.prefix + "bias", d.cout, &d.b)) return false;
+    }
+    if (!fp("encoder.norm_out.weight", e_c_last, &e_gn_g) || !fp("encoder.norm_out.bias", e_c_last, &e_gn_b)) return false;
+    const RawTensor *wc, *bc, *wq, *bq;
+    const size_t kc = static_cast<size_t>(e_c_last) * 9;
+    if (!get("encoder.conv_out.weight", z2 * kc, &wc) || !get("encoder.conv_out.bias", z2, &bc) ||
+        !get("quant_conv.weight", static_cast<size_t>(e2) * z2, &wq) || !get("quant_conv.bias", e2, &bq))
+      return false;
+    std::vector<float> hwc(z2 * kc), hbc(z2), hwq(static_cast<size_t>(e2) * z2), hbq(e2), fw(e2 * kc, 0.f), fb(32, 0.f);
+    CUDA_OK(cudaMemcpy(hwc.data(), wc->d, hwc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(hbc.data(), bc->d, hbc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(hwq.data(), wq->d, hwq.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(hbq.data(), bq->d, hbq.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int o = 0; o < e2; ++o) {
+      double b = hbq[o];
+      for (int m = 0; m < z2; ++m) {
+        const float q = hwq[static_cast<size_t>(o) * z2 + m];
+        b += static_cast<double>(q) * hbc[m];
+        for (size_t k = 0; k < kc; ++k) fw[o * kc + k] += q * hwc[m * kc + k];
+      }
+      fb[o] = static_cast<float>(b);
+    }
+    float* d_fw = dev_alloc<float>(fw.size());
+    ew_out = dev_alloc<bf16>(static_cast<size_t>(32) * kc, true);  // N padded to 32
+    eb_out = dev_alloc<float>(32, true);
+    if (!d_fw || !ew_out || !eb_out) return false;
+    CUDA_OK(cudaMemcpy(d_fw, fw.data(), fw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(eb_out, fb.data(), 32 * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(launch_pack_conv_weight(d_fw, e2, e_c_last, 3, 3, ew_out, static_cast<int>(kc), 0, 0));
+    has_encoder = true;
     return true;
   }
 
@@ -341,9 +516,10 @@ struct Vae {
   }
 
   bool conv_op(Ctx& c, const bf16* A, int H, int W, int cin, const bf16* A2, int K2, const bf16* Wt, int cout, float* out,
-               const float* bias, const float* residual) {
+               const float* bias, const float* residual, bool down = false) {
     GemmPlan p;
-    ConvGeom g{c.n_img, H, W, 9, 1};
+    ConvGeom g{c.n_img, H, W, 9, down ? 2 : 1};
+    g.asym_pad = down ? 1 : 0;
     if (!make_conv_plan(&p, A, g, cin, A2, K2, Wt, cout, OUT_F32, out, cout, bias, nullptr, 1, 0, residual, cout))
       return false;
     GemmPlan copy = p;
@@ -532,6 +708,144 @@ struct Vae {
     return true;
   }
 
+  // Downsample (model.py:68-87): F.pad(x, (0,1,0,1)) + conv3x3 stride 2 on the four parity planes of x
+  bool plan_down(Ctx& c, const VConv& w, const Buf& x, int H, int W, Buf* out) {
+    const int C = w.cin;
+    Buf planes = c.alloc(x.M, C, 2);
+    *out = c.alloc(static_cast<size_t>(x.M) / 4, w.cout, 4);
+    if (!c.dry) {
+      const float* px = c.ptr<float>(x);
+      bf16* pp = c.ptr<bf16>(planes);
+      const int n = c.n_img;
+      push(c, CLS_OTHER, 0, static_cast<double>(x.M) * C * 6,
+           [=](cudaStream_t s) { return launch_parity_split_bf16(px, n, H, W, C, pp, s); });
+      if (!conv_op(c, pp, H / 2, W / 2, C, nullptr, 0, w.w, w.cout, c.ptr<float>(*out), w.b, nullptr, true)) return false;
+    }
+    c.release(planes);
+    return true;
+  }
+
+  // Encoder.forward (model.py:518-545) + quant_conv: images [N][3][H][W] -> moments [N][2e][H/f][W/f]
+  bool build_enc_plan(Ctx& c, int N, int H, int W) {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    const int f = 1 << (cfg.n_levels - 1);
+    if (N < 1 || !pow2(H) || !pow2(W) || H < f || W < f) {
+      set_error("vae encoder: image H and W must be powers of two, at least 2^(levels-1)");
+      return false;
+    }
+    c.n_img = N;
+    Buf gnp;
+    gnp.bytes = groupnorm_partial_bytes(N);
+    gnp.off = c.arena.alloc(gnp.bytes);
+    gnp.valid = true;
+    if (!c.dry) {
+      c.gn_partial = c.ptr<float>(gnp);
+      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(N), 0, gnp.bytes - groupnorm_sync_offset(N)));
+    }
+    const size_t M0 = static_cast<size_t>(N) * H * W;
+    Buf a0 = c.alloc(M0, kpad_in, 2);
+    Buf h = c.alloc(M0, cfg.ch, 4);
+    if (!c.dry) {
+      Vae* self = this;
+      bf16* pa0 = c.ptr<bf16>(a0);
+      const int ic = cfg.out_ch, kp = kpad_in;
+      const float *eye = e_ident, *zero = e_zero;
+      push(c, CLS_OTHER, 0, static_cast<double>(M0) * (kp * 2 + ic * 4), [=](cudaStream_t s) {
+        return launch_vae_input_pack(self->io_img, N, ic, H, W, eye, zero, 1.0f, kp, pa0, s);
+      });
+      GemmPlan p;
+      if (!make_gemm_plan(&p, pa0, static_cast<int>(M0), kp, nullptr, 0, ew_in, cfg.ch, OUT_F32, c.ptr<float>(h), cfg.ch,
+                          eb_in, nullptr, 1, 0, nullptr, 0))
+        return false;
+      GemmPlan copy = p;
+      push(c, CLS_LINEAR, p.flops, 0, [copy](cudaStream_t s) { return launch_gemm(copy, s); });
+    }
+    c.release(a0);
+    Buf cur = h;
+    int curH = H, curW = W;
+    for (const VLayer& l : elayers) {
+      Buf nxt;
+      if (l.kind == V_RES) {
+        if (!plan_res(c, eres[l.idx], cur, curH, curW, &nxt)) return false;
+      } else if (l.kind == V_ATTN) {
+        if (!plan_attn(c, eattn[l.idx], cur, curH, curW, &nxt)) return false;
+      } else {
+        if (!plan_down(c, down[l.idx], cur, curH, curW, &nxt)) return false;
+        curH /= 2;
+        curW /= 2;
+      }
+      c.release(cur);
+      cur = nxt;
+    }
+    const size_t Mo = static_cast<size_t>(N) * curH * curW;
+    Buf a = c.alloc(Mo, e_c_last, 2);
+    if (!op_gn(c, cur, curH * curW, e_gn_g, e_gn_b, 1, a, nullptr)) return false;
+    c.release(cur);
+    Buf o32 = c.alloc(Mo, 32, 4);
+    if (!c.dry) {
+      if (!conv_op(c, c.ptr<bf16>(a), curH, curW, e_c_last, nullptr, 0, ew_out, 32, c.ptr<float>(o32), eb_out, nullptr))
+        return false;
+      Vae* self = this;
+      const float* po = c.ptr<float>(o32);
+      const int cout = 2 * cfg.embed_dim, oh = curH, ow = curW;
+      push(c, CLS_OTHER, 0, static_cast<double>(Mo) * cout * 8,
+           [=](cudaStream_t s) { return launch_vae_output(po, 32, N, cout, oh, ow, self->io_moments, s); });
+    }
+    c.release(a);
+    c.release(o32);
+    return true;
+  }
+
+  bool enc_workspace_bytes(int N, int H, int W, size_t* bytes) {
+    if (!has_encoder) {
+      set_error("vae: no encoder weights were loaded (encoder.*, quant_conv.*)");
+      return false;
+    }
+    Ctx c;
+    c.dry = true;
+    std::vector<Op> dummy;
+    c.ops = &dummy;
+    if (!build_enc_plan(c, N, H, W)) return false;
+    *bytes = c.arena.peak + 1024;
+    return true;
+  }
+
+  bool encode(const float* images, float* moments, int N, int H, int W, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!finalized) {
+      set_error("cap4d_b200_vae_finalize has not been called");
+      return false;
+    }
+    if (!(N == eN && H == eH && W == eW && ws == e_ws && ws_bytes == e_ws_bytes && !eops.empty())) {
+      size_t need = 0;
+      if (!enc_workspace_bytes(N, H, W, &need)) return false;
+      if (ws == nullptr || ws_bytes < need) {
+        set_error("workspace too small: need " + std::to_string(need) + " bytes");
+        return false;
+      }
+      eops.clear();
+      Ctx c;
+      c.dry = false;
+      c.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+      c.ops = &eops;
+      if (!build_enc_plan(c, N, H, W)) {
+        eops.clear();
+        return false;
+      }
+      eN = N, eH = H, eW = W, e_ws = ws, e_ws_bytes = ws_bytes;
+    }
+    io_img = images;
+    io_moments = moments;
+    for (size_t i = 0; i < eops.size(); ++i) {
+      cudaError_t e = eops[i].run(stream);
+      if (e != cudaSuccess) {
+        set_error("vae: launch of encoder op " + std::to_string(i) + " failed: " + cudaGetErrorString(e) + " / " +
+                  get_error());
+        return false;
+      }
+    }
+    return true;
+  }
+
   bool workspace_bytes(int N, int H, int W, size_t* bytes) {
     Ctx c;
     c.dry = true;
@@ -707,6 +1021,35 @@ int cap4d_b200_vae_decode_u8(void* handle, const float* z, uint8_t* images_bgr, 
   }
   return v->decode(z, nullptr, images_bgr, N, H, W, scale_factor, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream))
+             ? 0
+             : 6;
+}
+
+int cap4d_b200_vae_has_encoder(void* handle, int* yes) {
+  if (handle == nullptr || yes == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *yes = static_cast<Vae*>(handle)->has_encoder ? 1 : 0;
+  return 0;
+}
+
+int cap4d_b200_vae_encode_workspace_bytes(void* handle, int N, int H, int W, size_t* bytes) {
+  if (handle == nullptr || bytes == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  return static_cast<Vae*>(handle)->enc_workspace_bytes(N, H, W, bytes) ? 0 : 5;
+}
+
+int cap4d_b200_vae_encode(void* handle, const float* images, float* moments, int N, int H, int W, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (handle == nullptr || images == nullptr || moments == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  return static_cast<Vae*>(handle)->encode(images, moments, N, H, W, workspace, workspace_bytes,
+                                           static_cast<cudaStream_t>(stream))
              ? 0
              : 6;
 }

@@ -53,8 +53,8 @@ class B200VAEDecoder(torch.nn.Module):
         with torch.cuda.device(self._device):
             _lib.check(self._lib.cap4d_b200_vae_create(ctypes.byref(cfg), ctypes.byref(self._handle)), "vae_create")
             for name, t in state_dict.items():
-                if not name.startswith(("decoder.", "post_quant_conv.")):
-                    continue  # encoder / quant_conv / loss entries of a full AutoencoderKL state_dict
+                if not name.startswith(("decoder.", "post_quant_conv.", "encoder.", "quant_conv.")):
+                    continue  # loss / EMA entries of a full AutoencoderKL state_dict
                 t32 = t.detach().to(dtype=torch.float32).contiguous()
                 shape = (ctypes.c_int64 * max(1, t32.dim()))(*t32.shape)
                 _lib.check(self._lib.cap4d_b200_vae_load_weight(self._handle, name.encode(),
@@ -181,10 +181,78 @@ class B200VAEDecoder(torch.nn.Module):
 
     forward = decode_first_stage
 
+    # ---- encoder half: AutoencoderKL.encode (controlnet/ldm/models/autoencoder.py:82-85) -------------------------
+    @property
+    def has_encoder(self) -> bool:
+        """True when the state_dict carried the "encoder.*" / "quant_conv.*" entries."""
+        yes = ctypes.c_int()
+        _lib.check(self._lib.cap4d_b200_vae_has_encoder(self._handle, ctypes.byref(yes)), "vae_has_encoder")
+        return bool(yes.value)
+
+    @torch.no_grad()
+    def encode_moments(self, x: torch.Tensor, batch: int = 2) -> torch.Tensor:
+        """images [N, 3, H, W] in [-1, 1] -> posterior parameters [N, 2*embed_dim, H/f, W/f] (mean | logvar)."""
+        if x.dim() != 4 or x.shape[1] != self.config["out_ch"]:
+            raise ValueError("x must be [N, out_ch, H, W]")
+        xs = x.to(device=self._device, dtype=torch.float32).contiguous()
+        N, _, H, W = xs.shape
+        f = 2 ** (len(self.config["ch_mult"]) - 1)
+        out = torch.empty((N, 2 * self.config.get("embed_dim", self.config["z_channels"]), H // f, W // f),
+                          dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            for i in range(0, N, batch):
+                n = min(batch, N - i)
+                key = ("enc", n, H, W)
+                ws = self._ws.get(key)
+                if ws is None:
+                    nb = ctypes.c_size_t()
+                    _lib.check(self._lib.cap4d_b200_vae_encode_workspace_bytes(self._handle, n, H, W, ctypes.byref(nb)),
+                               "vae_encode_workspace_bytes")
+                    self._ws = {k: v for k, v in self._ws.items() if k[0] != "enc"}  # the library keeps one plan
+                    ws = self._ws[key] = torch.empty(nb.value + 2048, dtype=torch.uint8, device=self._device)
+                _lib.check(
+                    self._lib.cap4d_b200_vae_encode(self._handle, xs[i:i + n].data_ptr(), out[i:i + n].data_ptr(), n, H, W,
+                                                    ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
+                    "vae_encode")
+        return out
+
+    def encode(self, x: torch.Tensor) -> "DiagonalGaussian":
+        """AutoencoderKL.encode: returns the posterior (`.sample()`, `.mode()`, `.parameters`) like the reference."""
+        return DiagonalGaussian(self.encode_moments(x))
+
+    def encode_first_stage(self, x: torch.Tensor) -> torch.Tensor:
+        """MMLDM.get_input's latent (cap4d/mmdm/mmdm.py:60-63 -> ddpm.py:611-619): scale_factor * posterior.sample().
+        Accepts the reference's [B, T, 3, H, W] as well."""
+        lead = None
+        if x.dim() == 5:
+            lead = x.shape[:2]
+            x = x.reshape(-1, *x.shape[2:])
+        z = self.scale_factor * self.encode(x).sample()
+        return z.reshape(*lead, *z.shape[1:]) if lead is not None else z
+
     def num_launches(self) -> int:
         n = ctypes.c_int()
         _lib.check(self._lib.cap4d_b200_vae_num_launches(self._handle, ctypes.byref(n)), "vae_num_launches")
         return n.value
+
+
+class DiagonalGaussian:
+    """DiagonalGaussianDistribution (controlnet/ldm/modules/distributions/distributions.py:24-45) over device
+    moments: same attributes and the same RNG use (`torch.randn(shape)` on the CPU generator, then moved)."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self) -> torch.Tensor:
+        return self.mean + self.std * torch.randn(self.mean.shape).to(device=self.parameters.device)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
 
 
 def config_from_reference(first_stage_model) -> Dict:
@@ -200,6 +268,14 @@ def install_vae(mmldm, device=None) -> B200VAEDecoder:
     replaces `mmldm.first_stage_model.decode` in place.  ddpm.py has already divided by scale_factor there."""
     vae = B200VAEDecoder.from_reference(mmldm.first_stage_model, scale_factor=1.0, device=device)
     mmldm.first_stage_model.decode = vae.decode_first_stage
+    if vae.has_encoder:
+        # encode_first_stage (ddpm.py:832-834) -> first_stage_model.encode; get_first_stage_encoding (ddpm.py:656-663)
+        # checks isinstance against the reference's own posterior class, so hand the moments to that class
+        import sys
+
+        post_cls = getattr(sys.modules.get(type(mmldm.first_stage_model).__module__), "DiagonalGaussianDistribution",
+                           DiagonalGaussian)
+        mmldm.first_stage_model.encode = lambda x: post_cls(vae.encode_moments(x))
     return vae
 
 

@@ -162,8 +162,8 @@ typedef struct cap4d_b200_vae_config {
 
 /* Decoder.__init__ (model.py:546-604): derive the layer list (attn_resolutions = [] : mid-block attention only). */
 int cap4d_b200_vae_create(const cap4d_b200_vae_config* cfg, void** handle);
-/* fp32 parameters under the reference's state_dict names ("decoder.*", "post_quant_conv.*"; encoder entries
- * are not needed); host or device pointers. */
+/* fp32 parameters under the reference's state_dict names ("decoder.*", "post_quant_conv.*" are required;
+ * "encoder.*" + "quant_conv.*" are optional and enable cap4d_b200_vae_encode); host or device pointers. */
 int cap4d_b200_vae_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim);
 int cap4d_b200_vae_num_params(void* handle, int* n);
 int cap4d_b200_vae_param_info(void* handle, int index, char* name, int name_cap, int64_t* shape, int* ndim);
@@ -177,6 +177,16 @@ int cap4d_b200_vae_decode(void* handle, const float* z, float* images, int N, in
  * images_bgr: uint8 [N][8H][8W][3] = ((x + 1) / 2).clip(0, 1) * 255 truncated, channels reversed for cv2.imwrite. */
 int cap4d_b200_vae_decode_u8(void* handle, const float* z, uint8_t* images_bgr, int N, int H, int W, float scale_factor,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Encoder half (the rest of SURVEY 8f rank 1): AutoencoderKL.encode (controlnet/ldm/models/autoencoder.py:82-85) =
+ * Encoder.forward (controlnet/ldm/modules/diffusionmodules/model.py:518-545) + quant_conv, reached from
+ * MMLDM.get_input (cap4d/mmdm/mmdm.py:60-63) once per reference image.  Available when the "encoder.*" and
+ * "quant_conv.*" entries of the state_dict were loaded before finalize (they are optional as a whole).
+ * images: fp32 [N][out_ch][H][W] in [-1, 1]; moments: fp32 [N][2*embed_dim][H/f][W/f] with f = 2^(n_levels-1), i.e.
+ * DiagonalGaussianDistribution.parameters (mean | logvar); sampling and the scale factor stay with the caller. */
+int cap4d_b200_vae_has_encoder(void* handle, int* yes);
+int cap4d_b200_vae_encode_workspace_bytes(void* handle, int N, int H, int W, size_t* bytes);
+int cap4d_b200_vae_encode(void* handle, const float* images, float* moments, int N, int H, int W, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int cap4d_b200_vae_num_launches(void* handle, int* n);
 int cap4d_b200_vae_destroy(void* handle);
 

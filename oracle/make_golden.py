@@ -95,6 +95,25 @@ def golden_sampler(name, n_ref, n_gen, S, R_max, cfg_scale, seed):
     print(name, tuple(z.shape), "absmax", float(z.abs().max()))
 
 
+def golden_vae_encode(name, cfg, N, H, W, wseed, xseed):
+    """AutoencoderKL.encode of the unmodified reference: posterior parameters, mode and a sample."""
+    vae = RI.build_reference_vae(cfg)
+    sd = VO.init_vae_state_dict(cfg, seed=wseed)
+    sd.update(VO.init_vae_encoder_state_dict(cfg, seed=wseed))
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("loss") for k in missing), (missing, unexpected)
+    x = torch.tanh(torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(xseed)))
+    with torch.no_grad():
+        post = vae.encode(x)
+        torch.manual_seed(xseed + 1)
+        sample = post.sample()
+    mine = VO.vae_encode_moments(sd, cfg, x)
+    print(name, "moments", tuple(post.parameters.shape), "absmax", float(post.parameters.abs().max()),
+          "oracle err", float((mine - post.parameters).abs().max()))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), N=N, H=H, W=W, wseed=wseed, xseed=xseed,
+                        moments=post.parameters.numpy(), mode=post.mode().numpy(), sample=sample.numpy())
+
+
 def golden_vae(name, cfg, N, H, W, wseed, zseed):
     """decode_first_stage of the reference: z / scale_factor -> AutoencoderKL.decode (ddpm.py:822-830)."""
     vae = RI.build_reference_vae(cfg)
@@ -121,5 +140,7 @@ if __name__ == "__main__":
     golden_schedule()
     golden_sampler("sampler_r1", n_ref=1, n_gen=6, S=4, R_max=4, cfg_scale=2.0, seed=124)
     golden_sampler("sampler_r2", n_ref=3, n_gen=4, S=5, R_max=2, cfg_scale=2.0, seed=7)
+    golden_vae_encode("vae_enc_tiny_64", VO.TINY_VAE, N=2, H=64, W=64, wseed=0, xseed=2)
+    golden_vae_encode("vae_enc_tiny_64x128", VO.TINY_VAE, N=1, H=64, W=128, wseed=5, xseed=6)
     golden_vae("vae_tiny_h8", VO.TINY_VAE, N=2, H=8, W=8, wseed=0, zseed=1)
     golden_vae("vae_tiny_h16x8", VO.TINY_VAE, N=1, H=16, W=8, wseed=3, zseed=4)

@@ -147,6 +147,103 @@ def vae_decode(sd: Dict[str, torch.Tensor], cfg: dict, z: torch.Tensor, scale_fa
     return h
 
 
+# ---- encoder half: AutoencoderKL.encode (autoencoder.py:82-85) -----------------------------------------------
+#   Encoder.__init__ / forward           model.py:452-545   (attn_resolutions = []: mid-block attention only)
+#   Downsample.forward                   model.py:80-84     (F.pad (0,1,0,1) then conv3x3 stride 2, padding 0)
+#   quant_conv                           autoencoder.py:33,84
+#   DiagonalGaussianDistribution         controlnet/ldm/modules/distributions/distributions.py:24-45
+# Pinned against the unmodified reference module by oracle/make_golden.py -> tests/golden/vae_enc_*.npz.
+def vae_encoder_topology(cfg: dict):
+    """[(kind, prefix, cin, cout)] in execution order; kinds: conv_in, res, down, attn, out."""
+    ch, mult, nrb = cfg["ch"], tuple(cfg["ch_mult"]), cfg["num_res_blocks"]
+    layers = [("conv_in", "encoder.conv_in", cfg["out_ch"], ch)]
+    block_in = ch
+    for lvl in range(len(mult)):
+        block_out = ch * mult[lvl]
+        for i in range(nrb):
+            layers.append(("res", f"encoder.down.{lvl}.block.{i}", block_in, block_out))
+            block_in = block_out
+        if lvl != len(mult) - 1:
+            layers.append(("down", f"encoder.down.{lvl}.downsample.conv", block_in, block_in))
+    layers += [("res", "encoder.mid.block_1", block_in, block_in), ("attn", "encoder.mid.attn_1", block_in, block_in),
+               ("res", "encoder.mid.block_2", block_in, block_in), ("out", "encoder", block_in, 2 * cfg["z_channels"])]
+    return layers
+
+
+def vae_encoder_param_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    shapes: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    for kind, p, cin, cout in vae_encoder_topology(cfg):
+        if kind in ("conv_in", "down"):
+            shapes[p + ".weight"] = (cout, cin, 3, 3)
+            shapes[p + ".bias"] = (cout,)
+        elif kind == "res":
+            shapes[p + ".norm1.weight"] = (cin,)
+            shapes[p + ".norm1.bias"] = (cin,)
+            shapes[p + ".conv1.weight"] = (cout, cin, 3, 3)
+            shapes[p + ".conv1.bias"] = (cout,)
+            shapes[p + ".norm2.weight"] = (cout,)
+            shapes[p + ".norm2.bias"] = (cout,)
+            shapes[p + ".conv2.weight"] = (cout, cout, 3, 3)
+            shapes[p + ".conv2.bias"] = (cout,)
+            if cin != cout:
+                shapes[p + ".nin_shortcut.weight"] = (cout, cin, 1, 1)
+                shapes[p + ".nin_shortcut.bias"] = (cout,)
+        elif kind == "attn":
+            shapes[p + ".norm.weight"] = (cin,)
+            shapes[p + ".norm.bias"] = (cin,)
+            for n in ("q", "k", "v", "proj_out"):
+                shapes[f"{p}.{n}.weight"] = (cin, cin, 1, 1)
+                shapes[f"{p}.{n}.bias"] = (cin,)
+        elif kind == "out":
+            shapes["encoder.norm_out.weight"] = (cin,)
+            shapes["encoder.norm_out.bias"] = (cin,)
+            shapes["encoder.conv_out.weight"] = (cout, cin, 3, 3)
+            shapes["encoder.conv_out.bias"] = (cout,)
+    shapes["quant_conv.weight"] = (2 * cfg["embed_dim"], 2 * cfg["z_channels"], 1, 1)
+    shapes["quant_conv.bias"] = (2 * cfg["embed_dim"],)
+    return shapes
+
+
+def init_vae_encoder_state_dict(cfg: dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded synthetic encoder weights, same recipe as init_vae_state_dict."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in vae_encoder_param_shapes(cfg).items():
+        if "norm" in name and name.endswith(".weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) / fan_in ** 0.5
+    return sd
+
+
+@torch.no_grad()
+def vae_encode_moments(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.encode(x).parameters: images [N, 3, H, W] in [-1, 1] -> moments [N, 2e, H/f, W/f] (mean | logvar)."""
+    h = x
+    for kind, p, cin, cout in vae_encoder_topology(cfg):
+        if kind == "conv_in":
+            h = F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1)
+        elif kind == "res":
+            h = _res(sd, p, h)
+        elif kind == "attn":
+            h = _attn(sd, p, h)
+        elif kind == "down":
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+        elif kind == "out":
+            h = _gn_swish(h, sd, "encoder.norm_out")
+            h = F.conv2d(h, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def posterior_sample(moments: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """DiagonalGaussianDistribution.sample (distributions.py:24-37): mean + exp(0.5 * clamp(logvar, -30, 20)) * noise."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
 def to_uint8_bgr(x: torch.Tensor) -> torch.Tensor:
     """convert_and_save_latent_images (cap4d/inference/utils.py:131-137): [-1,1] CHW -> uint8 HWC, channels
     reversed for cv2.imwrite.  astype(uint8) truncates."""

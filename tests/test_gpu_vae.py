@@ -115,3 +115,68 @@ def test_convert_and_save_latent_images_end_to_end(cuda_device, tiny_vaes, tmp_p
     assert OUT.convert_and_save_latent_images(z, vae, cuda_device, tmp_path, batch=2, writers=2) == 5
     assert sorted(os.listdir(tmp_path / "images")) == [f"{i:05d}.png" for i in range(5)]
     assert np.array_equal(OUT.read_output_images(tmp_path)[..., ::-1], want)
+
+
+# ---- encoder half (AutoencoderKL.encode, autoencoder.py:82-85) -------------------------------------------------
+ENC_TOL = 2e-2  # max|a-b| / max|b| over the posterior parameters (mean | logvar), bf16 operands
+
+
+@pytest.fixture(scope="module")
+def tiny_full_vaes(cuda_device):
+    from cap4d_b200 import B200VAEDecoder
+
+    cache = {}
+
+    def get(seed):
+        if seed not in cache:
+            sd = VO.init_vae_state_dict(VO.TINY_VAE, seed=seed)
+            sd.update(VO.init_vae_encoder_state_dict(VO.TINY_VAE, seed=seed))
+            cache[seed] = (B200VAEDecoder(VO.TINY_VAE, sd, device=cuda_device), sd)
+        return cache[seed]
+
+    return get
+
+
+@pytest.mark.parametrize("name", ["vae_enc_tiny_64", "vae_enc_tiny_64x128"])
+def test_vae_encode_matches_reference_fixture(cuda_device, tiny_full_vaes, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    vae, _ = tiny_full_vaes(int(g["wseed"]))
+    assert vae.has_encoder
+    x = torch.tanh(torch.randn(int(g["N"]), 3, int(g["H"]), int(g["W"]),
+                               generator=torch.Generator().manual_seed(int(g["xseed"]))))
+    post = vae.encode(x.to(cuda_device))
+    want = torch.from_numpy(g["moments"])
+    assert post.parameters.shape == want.shape
+    err = O.max_rel_err(post.parameters.cpu(), want)
+    assert err <= ENC_TOL, f"{name}: encode parity {err:.3e}"
+    assert O.max_rel_err(post.mode().cpu(), torch.from_numpy(g["mode"])) <= ENC_TOL
+    torch.manual_seed(int(g["xseed"]) + 1)  # the reference draws the noise from the CPU generator
+    assert O.max_rel_err(post.sample().cpu(), torch.from_numpy(g["sample"])) <= ENC_TOL
+    # the decode path of the same handle is unaffected by the encoder weights
+    z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(1)) * 0.8
+    _, sd = tiny_full_vaes(int(g["wseed"]))
+    assert O.max_rel_err(vae.decode_first_stage(z.to(cuda_device)).cpu(), VO.vae_decode(sd, VO.TINY_VAE, z)) <= TOL
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 64, 64), (1, 128, 64), (1, 512, 512)])
+def test_vae_encode_matches_oracle(cuda_device, tiny_full_vaes, N, H, W):
+    """512 x 512 exercises the stride-2 conv on rows wider than one 128-pixel tile (the production 512 -> 256 step)."""
+    vae, sd = tiny_full_vaes(7)
+    x = torch.tanh(torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(H + W)))
+    got = vae.encode_moments(x.to(cuda_device), batch=2).cpu()
+    want = VO.vae_encode_moments(sd, VO.TINY_VAE, x)
+    err = O.max_rel_err(got, want)
+    assert err <= ENC_TOL, f"encode parity {err:.3e}"
+    # encode_first_stage: scale_factor * sample, [B, T, ...] accepted like MMLDM.get_input (mmdm.py:60-63)
+    torch.manual_seed(3)
+    z = vae.encode_first_stage(x[None].to(cuda_device))
+    torch.manual_seed(3)
+    want_z = VO.SCALE_FACTOR * VO.posterior_sample(want, torch.randn(N, 4, H // 8, W // 8))
+    assert z.shape == (1, N, 4, H // 8, W // 8) and O.max_rel_err(z[0].cpu(), want_z) <= ENC_TOL
+
+
+def test_vae_without_encoder_weights_refuses_to_encode(cuda_device, tiny_vaes):
+    vae, _ = tiny_vaes(0)
+    assert not vae.has_encoder
+    with pytest.raises(RuntimeError, match="no encoder weights"):
+        vae.encode_moments(torch.zeros(1, 3, 64, 64, device=cuda_device))

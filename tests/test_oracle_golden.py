@@ -122,3 +122,21 @@ def test_vae_production_census():
     assert sum(int(np.prod(s)) for s in shapes.values()) == 49_490_199
     kinds = [k for k, *_ in VO.vae_decoder_topology(VO.PRODUCTION_VAE)]
     assert kinds.count("res") == 14 and kinds.count("up") == 3 and kinds.count("attn") == 1
+
+
+@pytest.mark.parametrize("name", ["vae_enc_tiny_64", "vae_enc_tiny_64x128"])
+def test_vae_encode_oracle_matches_reference_fixture(name):
+    """AutoencoderKL.encode of the unmodified reference (oracle/make_golden.py:golden_vae_encode)."""
+    from oracle import vae_oracle as VO
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd = VO.init_vae_state_dict(VO.TINY_VAE, seed=int(g["wseed"]))
+    sd.update(VO.init_vae_encoder_state_dict(VO.TINY_VAE, seed=int(g["wseed"])))
+    x = torch.tanh(torch.randn(int(g["N"]), 3, int(g["H"]), int(g["W"]),
+                               generator=torch.Generator().manual_seed(int(g["xseed"]))))
+    m = VO.vae_encode_moments(sd, VO.TINY_VAE, x)
+    assert float((m - torch.from_numpy(g["moments"])).abs().max()) <= 3e-6
+    assert torch.equal(torch.from_numpy(g["mode"]), torch.from_numpy(g["moments"])[:, :4])
+    torch.manual_seed(int(g["xseed"]) + 1)
+    s = VO.posterior_sample(m, torch.randn(m.shape[0], 4, *m.shape[2:]))
+    assert float((s - torch.from_numpy(g["sample"])).abs().max()) <= 3e-6
