@@ -83,13 +83,50 @@ class B200VAEDecoder(torch.nn.Module):
         finally:
             lib.cap4d_b200_vae_destroy(h)
 
+    @staticmethod
+    def encoder_param_shapes(config: Mapping) -> Dict[str, tuple]:
+        """state_dict keys -> shapes of the optional encoder half (Encoder.__init__, model.py:466-516, + quant_conv)."""
+        ch, mult, nrb = int(config["ch"]), list(config["ch_mult"]), int(config["num_res_blocks"])
+        zc, e = int(config["z_channels"]), int(config.get("embed_dim", config["z_channels"]))
+        out: Dict[str, tuple] = {"encoder.conv_in.weight": (ch, int(config["out_ch"]), 3, 3), "encoder.conv_in.bias": (ch,)}
+
+        def res(p, cin, cout):
+            out.update({p + "norm1.weight": (cin,), p + "norm1.bias": (cin,), p + "conv1.weight": (cout, cin, 3, 3),
+                        p + "conv1.bias": (cout,), p + "norm2.weight": (cout,), p + "norm2.bias": (cout,),
+                        p + "conv2.weight": (cout, cout, 3, 3), p + "conv2.bias": (cout,)})
+            if cin != cout:
+                out.update({p + "nin_shortcut.weight": (cout, cin, 1, 1), p + "nin_shortcut.bias": (cout,)})
+
+        b = ch
+        for lvl, m in enumerate(mult):
+            for i in range(nrb):
+                res(f"encoder.down.{lvl}.block.{i}.", b, ch * m)
+                b = ch * m
+            if lvl != len(mult) - 1:
+                out[f"encoder.down.{lvl}.downsample.conv.weight"] = (b, b, 3, 3)
+                out[f"encoder.down.{lvl}.downsample.conv.bias"] = (b,)
+        res("encoder.mid.block_1.", b, b)
+        out.update({"encoder.mid.attn_1.norm.weight": (b,), "encoder.mid.attn_1.norm.bias": (b,)})
+        for n in ("q", "k", "v", "proj_out"):
+            out[f"encoder.mid.attn_1.{n}.weight"] = (b, b, 1, 1)
+            out[f"encoder.mid.attn_1.{n}.bias"] = (b,)
+        res("encoder.mid.block_2.", b, b)
+        out.update({"encoder.norm_out.weight": (b,), "encoder.norm_out.bias": (b,),
+                    "encoder.conv_out.weight": (2 * zc, b, 3, 3), "encoder.conv_out.bias": (2 * zc,),
+                    "quant_conv.weight": (2 * e, 2 * zc, 1, 1), "quant_conv.bias": (2 * e,)})
+        return out
+
     @classmethod
-    def random_init(cls, config: Mapping = VAE_CONFIG, seed: int = 0, device=None) -> "B200VAEDecoder":
+    def random_init(cls, config: Mapping = VAE_CONFIG, seed: int = 0, device=None,
+                    with_encoder: bool = False) -> "B200VAEDecoder":
         """Synthetic weights of the right architecture, generated on the GPU (benchmarks; no checkpoint offline)."""
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         g = torch.Generator(device=dev).manual_seed(seed)
         sd = {}
-        for name, shape in cls.param_shapes(config).items():
+        shapes = dict(cls.param_shapes(config))
+        if with_encoder:
+            shapes.update(cls.encoder_param_shapes(config))
+        for name, shape in shapes.items():
             if "norm" in name and name.endswith("weight"):
                 t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=dev)
             elif name.endswith("bias"):

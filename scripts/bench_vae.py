@@ -36,12 +36,47 @@ def decoder_flops(cfg, H, W):
     return fl + 2.0 * hw * cfg["out_ch"] * 9 * cin
 
 
+def bench_encode(args):
+    """AutoencoderKL.encode (reference images -> latents, once per reference view): images/s on the device and the
+    CPU path (oracle port) on one image."""
+    dev = torch.device("cuda:0")
+    vae = B200VAEDecoder.random_init(VAE_CONFIG, seed=0, device=dev, with_encoder=True)
+    n = args.encode
+    x = torch.tanh(torch.randn(n, 3, 512, 512, generator=torch.Generator().manual_seed(1))).to(dev)
+    for _ in range(2):
+        vae.encode_moments(x[:2], batch=2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m = vae.encode_moments(x, batch=2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    res = {"metric": "vae_encode_images_per_sec", "value": n / (ms * 1e-3), "unit": "images/s (512x512 -> 64x64 moments)",
+           "images": n, "batch": 2, "ms_per_image": ms / n, "moments_absmax": float(m.abs().max()), "dtype": "bf16",
+           "data": "synthetic"}
+    if not args.no_cpu:
+        from oracle import vae_oracle as VO  # cpu_baseline leg only
+
+        sd = VO.init_vae_state_dict(VO.PRODUCTION_VAE, seed=0)
+        sd.update(VO.init_vae_encoder_state_dict(VO.PRODUCTION_VAE, seed=0))
+        t0 = time.perf_counter()
+        VO.vae_encode_moments(sd, VO.PRODUCTION_VAE, x[:1].cpu())
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"one 512x512 image through oracle/vae_oracle.py: {dt:.1f} s"}
+    print(json.dumps(res))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=64)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--encode", type=int, default=0, help="also time AutoencoderKL.encode on this many 512x512 images")
     args = ap.parse_args()
+    if args.encode:
+        return bench_encode(args)
     dev = torch.device("cuda:0")
     vae = B200VAEDecoder.random_init(VAE_CONFIG, seed=0, device=dev)
     n, b = args.images, args.batch

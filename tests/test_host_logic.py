@@ -232,3 +232,11 @@ def test_vae_config_from_reference_module():
     assert cfg == dict(VO.TINY_VAE, ch_mult=tuple(VO.TINY_VAE["ch_mult"]))
     want = {k: tuple(v.shape) for k, v in vae.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
     assert B200VAEDecoder.param_shapes(cfg) == want
+
+
+def test_vae_encoder_param_shapes_match_oracle():
+    from cap4d_b200 import B200VAEDecoder
+    from oracle import vae_oracle as VO
+
+    for cfg in (VO.TINY_VAE, VO.PRODUCTION_VAE):
+        assert B200VAEDecoder.encoder_param_shapes(cfg) == dict(VO.vae_encoder_param_shapes(cfg))
