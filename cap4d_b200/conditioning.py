@@ -215,3 +215,53 @@ def install_conditioning(mmldm) -> B200CAP4DConditioning:
     cond = B200CAP4DConditioning.from_reference(mmldm.cond_stage_model)
     mmldm.cond_stage_model = cond
     return cond
+
+
+@torch.no_grad()
+def get_condition_from_dataloader(cond_stage_model, vae, dataloader, device, first_stage_key: str = "jpg",
+                                  control_key: str = "hint", to_cpu: bool = False, visualize: bool = False):
+    """get_condition_from_dataloader(model, dataloader, device) of cap4d/inference/utils.py:64-100 with the model's
+    two stages passed explicitly: `vae.encode_first_stage` plays MMLDM.get_input's encode (cap4d/mmdm/mmdm.py:47-66,
+    every frame, same RNG use) and `cond_stage_model(batch, unconditional=...)` its get_learned / get_unconditional
+    conditioning.  Returns the reference's dict ("cond_frames", "uncond_frames", "cond_vis_frames", "flame_params");
+    the frames stay on `device` unless to_cpu=True (the reference moves every frame to host memory and the sampler
+    uploads them again - B200StochasticIOSampler takes device tensors as they are)."""
+    from collections import defaultdict
+
+    cond_frames, uncond_frames, cond_vis_frames = defaultdict(list), defaultdict(list), defaultdict(list)
+    flame_params = []
+    dev = torch.device(device)
+    for batch in dataloader:
+        hint = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch[control_key].items()}
+        x = batch[first_stage_key].to(dev)
+        if x.dim() == 3:
+            x = x[..., None]
+        x = x.permute(0, 1, 4, 2, 3).contiguous()                       # 'b t h w c -> b t c h w'
+        hint["z"] = vae.encode_first_stage(x)                           # [b, t, 4, h/8, w/8]
+        c_uncond = cond_stage_model(hint, unconditional=True)
+        c_cond = cond_stage_model(hint, unconditional=False)
+        for key in c_cond:
+            cc = c_cond[key].reshape(-1, *c_cond[key].shape[2:])        # 'b t ... -> (b t) ...'
+            cu = c_uncond[key].reshape(-1, *c_uncond[key].shape[2:])
+            cond_frames[key].append(cc.cpu() if to_cpu else cc)
+            uncond_frames[key].append(cu.cpu() if to_cpu else cu)
+        if visualize:  # log_cond (utils.py:26-41)
+            vis = cond_stage_model.get_vis(c_cond["pos_enc"])
+            for key, v in vis.items():
+                b_ = v.shape[0]
+                v = v.reshape(-1, *v.shape[2:]).permute(0, 3, 1, 2)
+                v = torch.nn.functional.interpolate(v, scale_factor=8., mode="nearest").clamp(-1., 1.)
+                cond_vis_frames[key].append(v.permute(0, 2, 3, 1).cpu())                # '(b t) c h w -> (b t) h w c'
+                del b_
+        if "flame_params" in batch:
+            fp = batch["flame_params"]
+            for b in range(next(iter(fp.values())).shape[0]):
+                flame_params.append({k: (fp[k][b].cpu().numpy() if torch.is_tensor(fp[k]) else np.asarray(fp[k][b]))
+                                     for k in fp})
+    return {"cond_frames": cond_frames, "uncond_frames": uncond_frames, "cond_vis_frames": cond_vis_frames,
+            "flame_params": flame_params}
+
+
+def concat_frames(frames) -> dict:
+    """generate_images.py:104-108: one tensor per key."""
+    return {k: torch.cat(v, dim=0) for k, v in frames.items()}

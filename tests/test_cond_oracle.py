@@ -191,3 +191,44 @@ def test_camera_rows_match_oracle():
     for i in range(4):
         assert np.array_equal(rows[i], CO.camera_rows(g["crop_boxes"][i], g["intr"][i], g["extr"][i], g["ref_extr"],
                                                       int(g["S"])))
+
+
+def test_get_condition_from_dataloader_glue():
+    """Host glue of cap4d/inference/utils.py:64-100 with stand-in stages (the real ones need a GPU): key set, the
+    'b t ... -> (b t) ...' flattening, z hand-over, flame parameter unpacking."""
+    from cap4d_b200.conditioning import concat_frames, get_condition_from_dataloader
+
+    S = 8
+
+    class Cond:
+        def __call__(self, hint, unconditional=True):
+            B, T = hint["verts_2d"].shape[:2]
+            pe = torch.zeros(B, T, S, S, 50) if unconditional else torch.ones(B, T, S, S, 50) * hint["verts_2d"].mean()
+            return {"pos_enc": pe, "z_input": hint["z"] * (0. if unconditional else 1.),
+                    "ref_mask": hint["reference_mask"][:, :, None]}
+
+        def get_vis(self, enc):
+            return {"ray_map": enc[..., 45:48]}
+
+    class Vae:
+        def encode_first_stage(self, x):
+            assert x.shape[2] == 3  # b t c h w
+            return x[:, :, :1, ::8, ::8].repeat(1, 1, 4, 1, 1) + 1.0
+
+    def frame(i, is_ref):
+        return {"jpg": torch.full((1, 1, 64, 64, 3), float(i)),
+                "hint": {"verts_2d": torch.full((1, 1, 5, 3), float(i)), "offsets_3d": torch.zeros(1, 1, 5, 3),
+                         "reference_mask": torch.full((1, 1, S, S), float(is_ref))},
+                "flame_params": {"fx": torch.full((1, 1, 1), 100.0 + i), "extr": torch.eye(4)[None, None] * i}}
+
+    out = get_condition_from_dataloader(Cond(), Vae(), [frame(0, True), frame(1, False), frame(2, False)], "cpu",
+                                        visualize=True)
+    cf, uf = concat_frames(out["cond_frames"]), concat_frames(out["uncond_frames"])
+    assert set(cf) == {"pos_enc", "z_input", "ref_mask"}
+    assert cf["pos_enc"].shape == (3, S, S, 50) and cf["z_input"].shape == (3, 4, S, S) and cf["ref_mask"].shape == (3, 1, S, S)
+    assert [float(cf["pos_enc"][i].mean()) for i in range(3)] == [0.0, 1.0, 2.0]
+    assert [float(cf["z_input"][i].mean()) for i in range(3)] == [1.0, 2.0, 3.0] and float(uf["z_input"].abs().max()) == 0
+    assert float(uf["pos_enc"].abs().max()) == 0 and torch.equal(uf["ref_mask"], cf["ref_mask"])
+    assert len(out["flame_params"]) == 3 and out["flame_params"][2]["fx"].shape == (1, 1)
+    assert float(out["flame_params"][1]["fx"][0, 0]) == 101.0
+    assert out["cond_vis_frames"]["ray_map"][0].shape == (1, 8 * S, 8 * S, 3)
