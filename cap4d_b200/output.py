@@ -61,27 +61,32 @@ def to_uint8_bgr(x_samples: torch.Tensor) -> np.ndarray:
 
 
 def convert_and_save_latent_images(latents: torch.Tensor, model, device, output_dir, batch: int = 8,
-                                   writers: int = 8, start_index: int = 0) -> int:
+                                   writers: int = 8, start_index: int = 0, rank: int = 0, world: int = 1) -> int:
     """convert_and_save_latent_images(latents, model, device, output_dir) of cap4d/inference/utils.py:125-137.
 
     `model` is a B200VAEDecoder, or an MMLDM whose first stage has been installed with `install_vae` / carries a
     `b200_vae` attribute; `device` is accepted for signature compatibility (the decoder is bound to its GPU).
-    Returns the number of files written."""
+    With one process per GPU every rank holds all latents after the sampler's last all-gather: rank r of `world`
+    decodes and writes the contiguous block r of the views (file names keep the global index; no collective).
+    Returns the number of files this rank wrote."""
     vae = getattr(model, "b200_vae", model)
     if not hasattr(vae, "decode_to_uint8_bgr"):
         raise RuntimeError("cap4d_b200: convert_and_save_latent_images needs a B200VAEDecoder (there is no CPU path)")
     out_img_dir = Path(output_dir) / "images"
     out_img_dir.mkdir(exist_ok=True)
-    n = latents.shape[0]
+    if not (0 <= rank < world):
+        raise ValueError("rank must be in [0, world)")
+    per = (latents.shape[0] + world - 1) // world
+    lo, hi = min(rank * per, latents.shape[0]), min((rank + 1) * per, latents.shape[0])
     pending = []
     with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
-        for i in range(0, n, batch):
-            imgs = vae.decode_to_uint8_bgr(latents[i:i + batch], batch=batch).numpy()
+        for i in range(lo, hi, batch):
+            imgs = vae.decode_to_uint8_bgr(latents[i:min(i + batch, hi)], batch=batch).numpy()
             for j in range(imgs.shape[0]):
                 pending.append(pool.submit(write_png_bgr, out_img_dir / f"{start_index + i + j:05d}.png", imgs[j]))
         for f in pending:
             f.result()
-    return n
+    return hi - lo
 
 
 def save_flame_params(flame_params: Sequence[Mapping[str, np.ndarray]], output_dir) -> None:

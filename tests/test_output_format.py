@@ -92,3 +92,19 @@ def test_save_visualization_layout(tmp_path):
     assert sorted(os.listdir(tmp_path / "condition_vis" / "ray_map")) == ["00000.jpg", "00001.jpg"]
     a = OUT.cv2.imread(str(tmp_path / "condition_vis" / "ray_map" / "00000.jpg"))
     assert a.shape == (16, 16, 3) and abs(int(a.mean()) - 127) <= 1
+
+
+def test_ranks_write_disjoint_blocks_with_global_names(gold, tmp_path):
+    """One process per GPU: every rank writes its block of the views; together they produce the reference's files."""
+    n = gold["x_samples"].shape[0]
+    latents = torch.arange(n, dtype=torch.float32).view(n, 1, 1, 1)
+    counts = [OUT.convert_and_save_latent_images(latents, _StubDecoder(gold["x_samples"]), "cuda:0", tmp_path, batch=2,
+                                                 rank=r, world=3) for r in range(3)]
+    assert counts == [2, 2, 1] and sum(counts) == n
+    assert sorted(os.listdir(tmp_path / "images")) == list(gold["file_names"])
+    assert np.array_equal(OUT.read_output_images(tmp_path)[..., ::-1], gold["pixels_bgr"])
+    (tmp_path / "solo").mkdir()
+    assert OUT.convert_and_save_latent_images(latents, _StubDecoder(gold["x_samples"]), "cuda:0", tmp_path / "solo",
+                                              rank=7, world=8) == 0  # more ranks than views: nothing to do
+    with pytest.raises(ValueError):
+        OUT.convert_and_save_latent_images(latents, _StubDecoder(gold["x_samples"]), "cuda:0", tmp_path, rank=3, world=3)
