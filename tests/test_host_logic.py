@@ -180,6 +180,108 @@ def test_sampler_rejects_indivisible_view_count():
 
 
 # ---------------------------------------------------------------------------------------------
+# ragged group shapes against the oracle sampler, with a cheap cross-view stand-in for the U-Net (a view's
+# output depends on every view of its group, its conditioning and the timestep, so a wrong grouping, a
+# wrong reference draw or a wrong scatter changes the result)
+# ---------------------------------------------------------------------------------------------
+def _toy_eps(x, t, control):
+    ctx = (x + control["z_input"]).mean(dim=1, keepdim=True)                       # couples the views of a group
+    pe = control["pos_enc"].mean(dim=-1)[:, :, None]                               # [B, V, 1, h, w]
+    tt = (t.to(torch.float32) / 1000.0)[:, :, None, None, None]
+    return torch.tanh(0.3 * x + 0.2 * ctx + 0.1 * pe + 0.05 * control["ref_mask"] + tt)
+
+
+class _ToyBackend(_TorchBackend):
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.calls = []
+
+    def eps(self, x_in, t_in, control, n_ref_views=0):
+        assert float(control["ref_mask"][:, :n_ref_views].min()) == 1.0
+        assert float(control["ref_mask"][:, n_ref_views:].max()) == 0.0
+        self.calls.append(x_in.shape[0] // 2)
+        return _toy_eps(x_in, t_in, control)
+
+
+RAGGED = [  # n_ref, n_gen, V, R_max, groups_per_call, eta
+    (1, 6, 4, 4, 5, 0.0),    # 2 groups, groups_per_call larger than the group count
+    (5, 4, 4, 2, 3, 0.0),    # more references than R_max: 2 of 5 drawn per group and step
+    (3, 3, 4, 4, 2, 0.0),    # R = 3: a single generated view per group, 3 groups in calls of 2 + 1
+    (2, 8, 6, 4, 3, 0.5),    # eta > 0 (only the eps coefficient changes, sampler.py:215-231)
+    (10, 12, 8, 4, 2, 0.0),  # multi_ref.yaml's shape: 4 of 10 references, 3 groups
+]
+
+
+def _ragged_inputs(n_ref, n_gen, seed=5):
+    cfg = dict(in_channels=4, condition_channels=6)
+    return O.make_sampler_conditioning(cfg, n_ref, n_gen, 4, 4, seed=seed)
+
+
+def _run_ragged(case, backend):
+    from cap4d_b200 import B200StochasticIOSampler
+
+    n_ref, n_gen, V, R_max, gpc, eta = case
+    rc, ru, gc, gu = _ragged_inputs(n_ref, n_gen)
+    torch.manual_seed(9)
+    np.random.seed(9)
+    sampler = B200StochasticIOSampler(_Model(), groups_per_call=gpc, backend=backend)
+    return sampler.sample(S=5, ref_cond=rc, ref_uncond=ru, gen_cond=gc, gen_uncond=gu, latent_shape=(4, 4, 4), V=V,
+                          R_max=R_max, cfg_scale=1.7, eta=eta)
+
+
+@pytest.mark.parametrize("case", RAGGED)
+def test_sampler_ragged_groups_match_oracle_sampler(case):
+    n_ref, n_gen, V, R_max, gpc, eta = case
+    rc, ru, gc, gu = _ragged_inputs(n_ref, n_gen)
+    torch.manual_seed(9)
+    np.random.seed(9)
+    want = O.stochastic_io_sample(_toy_eps, _Model().alphas_cumprod.numpy(), 5, rc, ru, gc, gu, (4, 4, 4), V=V,
+                                  R_max=R_max, cfg_scale=1.7, eta=eta)
+    be = _ToyBackend()
+    z = _run_ragged(case, be)
+    assert z.shape == want.shape == (n_gen, 4, 4, 4)
+    assert O.max_rel_err(z, want) < 1e-5
+    n_its = n_gen // (V - min(n_ref, R_max))
+    per_step = [min(gpc, n_its - c0) for c0 in range(0, n_its, gpc)]
+    assert be.calls == per_step * 5  # every group exactly once per step, batched groups_per_call at a time
+
+
+def _ragged_rank_main(rank, world, port, case, out_dir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        be = _ToyBackend()
+        z = _run_ragged(case, be)
+        torch.save((z, sum(be.calls)), os.path.join(out_dir, f"z{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,case", [(3, (1, 12, 4, 4, 1, 0.0)),    # 4 groups on 3 ranks: shares of 2, 1, 1
+                                        (3, (10, 8, 8, 4, 2, 0.0))])   # 2 groups on 3 ranks: one rank idles
+def test_sampler_ragged_rank_shares_gloo(tmp_path, world, case):
+    """Ranks with unequal (or no) shares of a step's groups: the padded all-gather must still leave every rank
+    with the single-process latents."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_ragged_rank_main, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    want = _run_ragged(case, _ToyBackend())
+    n_its = case[1] // (case[2] - min(case[0], case[3]))
+    groups = 0
+    for r in range(world):
+        z, g = torch.load(tmp_path / f"z{r}.pt")
+        assert torch.equal(z, want), f"rank {r}"   # same arithmetic per group: bit-identical to one process
+        groups += g
+    assert groups == n_its * 5
+
+
+# ---------------------------------------------------------------------------------------------
 # N > 1: two gloo ranks on CPU must reproduce the single-process result
 # ---------------------------------------------------------------------------------------------
 def _free_port():
