@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the schedule code applies np.sqrt to torch tensors exactly like the reference (sampler.py:215-229) so that the
+    # float32/float64 promotion is bit-identical; numpy 2 warns about torch's __array_wrap__ signature on every call
+    config.addinivalue_line("filterwarnings", "ignore:__array_wrap__ must accept context:DeprecationWarning")
 
 
 @pytest.fixture(scope="session")
