@@ -45,7 +45,18 @@ constexpr int TM_COLS = 512;
 constexpr int TM_S = 0;     // S_X (fp32 128x128)   at   0 + 128 x
 constexpr int TM_O = 256;   // O_X (fp32 128x64)    at 256 +  64 x
 constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
-constexpr int REGS_CTRL = 40, REGS_SOFTMAX = 104;  // pool = 640 * 96 at launch: 128 * (96 - 40) >= 512 * (104 - 96)
+// pool = 640 * 96 at launch: 128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96) or the kernel deadlocks.
+// Overridable for A/B builds (scripts/attn_variants.sh): -DCAP4D_ATTN_REGS_CTRL=32 -DCAP4D_ATTN_REGS_SOFTMAX=112
+#ifndef CAP4D_ATTN_REGS_CTRL
+#define CAP4D_ATTN_REGS_CTRL 40
+#endif
+#ifndef CAP4D_ATTN_REGS_SOFTMAX
+#define CAP4D_ATTN_REGS_SOFTMAX 104
+#endif
+constexpr int REGS_CTRL = CAP4D_ATTN_REGS_CTRL, REGS_SOFTMAX = CAP4D_ATTN_REGS_SOFTMAX;
+static_assert(REGS_CTRL % 8 == 0 && REGS_SOFTMAX % 8 == 0 && REGS_CTRL >= 24 && REGS_SOFTMAX <= 256 &&
+                  128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96),
+              "setmaxnreg budget: the control warpgroup must release what the softmax warpgroups take");
 constexpr float RESCALE_LOG2 = 8.0f;  // O / l are only rescaled when the row max grew by more than 2^8
 
 struct AttnBars {
