@@ -47,6 +47,9 @@ constexpr int TM_O = 256;   // O_X (fp32 128x64)    at 256 +  64 x
 constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
 // pool = 640 * 96 at launch: 128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96) or the kernel deadlocks.
 // Overridable for A/B builds (scripts/attn_variants.sh): -DCAP4D_ATTN_REGS_CTRL=32 -DCAP4D_ATTN_REGS_SOFTMAX=112
+#ifndef CAP4D_ATTN_PACKED_F32X2
+#define CAP4D_ATTN_PACKED_F32X2 0
+#endif
 #ifndef CAP4D_ATTN_REGS_CTRL
 #define CAP4D_ATTN_REGS_CTRL 40
 #endif
@@ -167,8 +170,27 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     }
   }
   ATTN_STAMP(3);
-  float rs0 = 0.f, rs1 = 0.f;
   uint32_t pk[HK / 2];
+#if CAP4D_ATTN_PACKED_F32X2
+  // A/B build (not the default): scale-subtract and row sums as packed f32x2 (FFMA2 / FADD2: 2.75 instead of
+  // 3.75 issue slots per score)
+  {
+    const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_used, -m_used);
+    f32x2 rs2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < HK; i += 2) {
+      float a0, a1;
+      unpack2(fma2(pack2(s[i], s[i + 1]), sc2, nm2), a0, a1);
+      const float p0 = ex2f(a0), p1 = ex2f(a1);
+      rs2 = add2(rs2, pack2(p0, p1));
+      pk[i >> 1] = pack_bf16x2(p0, p1);
+    }
+    float rs0, rs1;
+    unpack2(rs2, rs0, rs1);
+    l_run += rs0 + rs1;
+  }
+#else
+  float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
   for (int i = 0; i < HK; i += 2) {
     const float p0 = ex2f(fmaf(s[i], scale_log2, -m_used));
@@ -178,6 +200,7 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     pk[i >> 1] = pack_bf16x2(p0, p1);
   }
   l_run += rs0 + rs1;
+#endif
   ATTN_STAMP(4);
   if (!pv_waited) {
     // P_X may only be overwritten once the PV MMA of tile j-1 has consumed it (long done by now)
