@@ -76,12 +76,46 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img) {
   return g;
 }
 
+// A/B builds only (-DCAP4D_GN_CACHE_HINTS=1, not the default): L2 eviction priorities for the two-pass GroupNorm -
+// first-pass reads are kept (evict_last: the same rows are read again after the image barrier), second-pass reads and
+// the bf16 outputs are marked evict_first so that they do not push the waiting inputs out.
+#ifndef CAP4D_GN_CACHE_HINTS
+#define CAP4D_GN_CACHE_HINTS 0
+#endif
+#if CAP4D_GN_CACHE_HINTS
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_hint(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint(bf16* ptr, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(ptr), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+#endif
+
 // row2 = row + x2_shift: the second source may hold more images than the first (see launch_groupnorm)
 __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2,
-                                          size_t row, size_t row2, int c) {
+                                          size_t row, size_t row2, int c, uint64_t pol = 0) {
   // c is a multiple of 4 and C1 is a multiple of 4, so a quad never straddles the seam
+#if CAP4D_GN_CACHE_HINTS
+  if (c < C1) return ld_hint(x1 + row * C1 + c, pol);
+  return ld_hint(x2 + row2 * C2 + (c - C1), pol);
+#else
   if (c < C1) return __ldg(reinterpret_cast<const float4*>(x1 + row * C1 + c));
   return __ldg(reinterpret_cast<const float4*>(x2 + row2 * C2 + (c - C1)));
+#endif
 }
 
 // ---- GroupNorm (+SiLU), one kernel ---------------------------------------------------------------
@@ -117,6 +151,11 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
   const size_t img_row = static_cast<size_t>(n) * hw;
   const size_t img_row2 = (x2_G > 0) ? static_cast<size_t>((n / x2_G) * x2_V + x2_R + n % x2_G) * hw : img_row;
 
+#if CAP4D_GN_CACHE_HINTS
+  const uint64_t pol1 = l2_policy_evict_last(), pol2 = l2_policy_evict_first();
+#else
+  const uint64_t pol1 = 0, pol2 = 0;
+#endif
   // ---------------- phase 1: statistics of this chunk ----------------
   {
     float sum[NQI][4], sq[NQI][4];
@@ -130,7 +169,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-        for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4);
+        for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4, pol1);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
@@ -144,7 +183,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     for (; r < r1; r += TY) {
 #pragma unroll
       for (int qi = 0; qi < NQI; ++qi) {
-        const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4);
+        const float4 v = ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4, pol1);
         sum[qi][0] += v.x; sq[qi][0] = fmaf(v.x, v.x, sq[qi][0]);
         sum[qi][1] += v.y; sq[qi][1] = fmaf(v.y, v.y, sq[qi][1]);
         sum[qi][2] += v.z; sq[qi][2] = fmaf(v.z, v.z, sq[qi][2]);
@@ -243,9 +282,15 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
       y2 = silu_f(y2);
       y3 = silu_f(y3);
     }
+#if CAP4D_GN_CACHE_HINTS
+    st_hint(out + row * C + c, make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3)), pol2);
+    if (raw_out != nullptr)
+      st_hint(raw_out + row * C + c, make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)), pol2);
+#else
     *reinterpret_cast<uint2*>(out + row * C + c) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
     if (raw_out != nullptr)
       *reinterpret_cast<uint2*>(raw_out + row * C + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+#endif
   };
   int r = r0 + ty;
   for (; r + (UNROLL - 1) * TY < r1; r += UNROLL * TY) {
@@ -253,7 +298,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4);
+      for (int qi = 0; qi < NQI; ++qi) v[u][qi] = ld_quad(x1, x2, C1, C2, img_row + r + u * TY, img_row2 + r + u * TY, (tx + qi * TX) * 4, pol2);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
@@ -261,7 +306,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
   }
   for (; r < r1; r += TY) {
 #pragma unroll
-    for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4));
+    for (int qi = 0; qi < NQI; ++qi) emit(img_row + r, qi, ld_quad(x1, x2, C1, C2, img_row + r, img_row2 + r, (tx + qi * TX) * 4, pol2));
   }
   // ---------------- the last chunk of the image resets its counters for the next launch ----------------
   __syncthreads();

@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.." || exit 1
 cp cap4d_b200/libcap4d_b200.so /tmp/lib_orig.so
 for v in gpurun_variants/lib_*.so; do
+  case "$v" in *lib_gn_*) continue;; esac
   cp "$v" cap4d_b200/libcap4d_b200.so
   echo "== $v"
   [ -z "$SKIP_TESTS" ] && timeout 200 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -p no:cacheprovider -k attention 2>&1 | tail -1
