@@ -48,7 +48,7 @@ constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
 // pool = 640 * 96 at launch: 128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96) or the kernel deadlocks.
 // Overridable for A/B builds (scripts/attn_variants.sh): -DCAP4D_ATTN_REGS_CTRL=32 -DCAP4D_ATTN_REGS_SOFTMAX=112
 #ifndef CAP4D_ATTN_PACKED_F32X2
-#define CAP4D_ATTN_PACKED_F32X2 0
+#define CAP4D_ATTN_PACKED_F32X2 1  // 0 = the scalar FFMA / FADD softmax of round 1 (kept for A/B builds)
 #endif
 #ifndef CAP4D_ATTN_POLY_EVERY
 #define CAP4D_ATTN_POLY_EVERY 0  // needs CAP4D_ATTN_PACKED_F32X2: every N-th pair of scores uses exp2_poly_pair
@@ -58,6 +58,15 @@ constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
 #endif
 #ifndef CAP4D_ATTN_REGS_SOFTMAX
 #define CAP4D_ATTN_REGS_SOFTMAX 104
+#endif
+// Diagnostic builds (WRONG results, scripts/attn_diag.sh): what does the kernel cost without the row max / exchange,
+// without the exponentials, without both (= the TMEM / MMA / barrier skeleton)?  Round 2, level-0 shape, cycles
+// per KV tile pair: shipped 2850, no max 2450, no exp 2250, neither 2000 (profiles/r02_attn_diag.log).
+#ifndef CAP4D_ATTN_DIAG_NOMAX
+#define CAP4D_ATTN_DIAG_NOMAX 0
+#endif
+#ifndef CAP4D_ATTN_DIAG_NOEXP
+#define CAP4D_ATTN_DIAG_NOEXP 0
 #endif
 constexpr int REGS_CTRL = CAP4D_ATTN_REGS_CTRL, REGS_SOFTMAX = CAP4D_ATTN_REGS_SOFTMAX;
 static_assert(REGS_CTRL % 8 == 0 && REGS_SOFTMAX % 8 == 0 && REGS_CTRL >= 24 && REGS_SOFTMAX <= 256 &&
@@ -81,9 +90,13 @@ struct AttnBars {
 };
 
 __device__ __forceinline__ float ex2f(float x) {
+#if CAP4D_ATTN_DIAG_NOEXP
+  return x;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // A/B builds only (CAP4D_ATTN_POLY_EVERY): 2^x for two arguments without the MUFU.  x = n + f with n = round(x)
@@ -159,6 +172,10 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     for (int i = 0; i < HK; ++i)
       if (half * HK + i >= valid) s[i] = -INFINITY;
   }
+#if CAP4D_ATTN_DIAG_NOMAX
+  bool pv_waited = (j == 0);
+  if (j == 0) m_used = 0.f;
+#else
   float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
   for (int i = 4; i < HK; i += 4) {
@@ -191,11 +208,12 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
       if (grow) m_used = m_new;
     }
   }
+#endif
   ATTN_STAMP(3);
   uint32_t pk[HK / 2];
 #if CAP4D_ATTN_PACKED_F32X2
-  // A/B build (not the default): scale-subtract and row sums as packed f32x2 (FFMA2 / FADD2: 2.75 instead of
-  // 3.75 issue slots per score)
+  // scale-subtract and row sums as packed f32x2 (FFMA2 / FADD2: 2.75 instead of 3.75 issue slots per score;
+  // +4 % on the level-0 / level-1 shapes, profiles/r02_attn_variants.log)
   {
     const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_used, -m_used);
     f32x2 rs2 = pack2(0.f, 0.f);

@@ -43,6 +43,17 @@ __global__ void k(float* out, int iters, long long* cyc) {
           asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2) : "l"(ss));
           unsigned u = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632); m += __uint_as_float(u);
           a[i-1] = e0; a[i] = e1; } }
+      if (MODE == 13 || MODE == 14 || MODE == 15) { if (i & 1) { // the kernel's packed loop: FFMA2 + 2 EX2 + FADD2 + F2FP (13), without F2FP (14), PRMT pack (15)
+          unsigned long long xx, cc = 0x3f7fbe773f7fbe77ull, dd = 0xbdcccccdbdcccccdull, ss;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(a[i-1]), "f"(a[i]));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(xx) : "l"(cc), "l"(dd));
+          float x0, x1; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+          float e0 = ex2(x0), e1 = ex2(x1);
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(ss) : "f"(e0), "f"(e1));
+          asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2) : "l"(ss));
+          if (MODE == 13) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(e1), "f"(e0)); m += __uint_as_float(u); }
+          if (MODE == 15) { unsigned u = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632); m += __uint_as_float(u); }
+          a[i-1] = e0; a[i] = e1; } }
       if (MODE == 5) { float e = ex2(fmaf(a[i], 0.999f, -0.1f)); s += e; a[i] = e; asm volatile("max.f32 %0, %0, %1;" : "+f"(m) : "f"(e)); }
     }
   }
@@ -67,7 +78,7 @@ void run(const char* name, int warps) {
 }
 
 int main() {
-  for (int w : {4, 8, 16}) {
+  for (int w : {4, 8, 12, 16}) {
     run<0>("MUFU.EX2", w);
     run<1>("FFMA", w);
     run<4>("FMNMX", w);
@@ -80,6 +91,9 @@ int main() {
     run<7>("FFMA+EX2+FADD+F2FP/2", w);
     run<11>("FFMA+EX2+FADD+intpack", w);
     run<12>("FFMA2+EX2+FADD2+intpack", w);
+    run<13>("FFMA2+EX2+FADD2+F2FP/2", w);
+    run<14>("FFMA2+EX2+FADD2", w);
+    run<15>("FFMA2+EX2+FADD2+PRMT(trunc)", w);
   }
   return 0;
 }

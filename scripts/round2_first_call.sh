@@ -6,5 +6,5 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 echo "=== L2 producer->consumer reuse"; timeout 200 python scripts/l2_reuse.py > gpurun_out/r02_l2_reuse.jsonl 2> gpurun_out/r02_l2_reuse.err; cat gpurun_out/r02_l2_reuse.jsonl | cut -c1-400
-echo "=== attention variants"; timeout 600 scripts/attn_variants.sh > gpurun_out/r02_attn_variants.log 2>&1; grep -E "^==|passed|failed|n_seq=80|n_seq=10" gpurun_out/r02_attn_variants.log
+echo "=== attention variants"; timeout 600 scripts/attn_variants.sh > gpurun_out/r02_attn_variants.log 2>&1; grep -E "^==|passed|failed|n_seq=80|n_seq=10|TFLOP" gpurun_out/r02_attn_variants.log
 echo "=== GroupNorm variants"; timeout 400 scripts/gn_variants.sh > gpurun_out/r02_gn_variants.log 2>&1; grep -E "^==|passed|failed|hw=4096" gpurun_out/r02_gn_variants.log
