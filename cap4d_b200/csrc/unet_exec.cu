@@ -854,8 +854,20 @@ struct Unet {
       c.emb_all = c.ptr<float>(emb);
       c.emb_gen = (c.R > 0) ? c.ptr<float>(embg) : nullptr;
       c.gn_partial = c.ptr<float>(gnp);
-      // the GroupNorm kernel's per-image barrier counters start at zero (it re-zeroes them itself)
-      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(n_img), 0, gnp.bytes - groupnorm_sync_offset(n_img)));
+      // The GroupNorm kernel's per-image counters must be zero when a forward starts.  Every launch leaves them
+      // zeroed, but a plan can be parked while its workspace is reused by the caller (or a launch can have been
+      // aborted), so they are cleared on the caller's stream at the head of every forward (a few hundred bytes).
+      {
+        uint8_t* sync_ptr = c.base + gnp.off + groupnorm_sync_offset(n_img);
+        const size_t sync_bytes = gnp.bytes - groupnorm_sync_offset(n_img);
+        Op op;
+        op.cls = CLS_OTHER;
+        op.launches = 0;
+        op.flops = 0;
+        op.bytes = static_cast<double>(sync_bytes);
+        op.run = [=](cudaStream_t s) { return cudaMemsetAsync(sync_ptr, 0, sync_bytes, s); };
+        c.ops->push_back(op);
+      }
     }
     const int M0 = n_img * H * W;
     // ---- input stage

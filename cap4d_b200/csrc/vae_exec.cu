@@ -650,7 +650,20 @@ struct Vae {
     gnp.valid = true;
     if (!c.dry) {
       c.gn_partial = c.ptr<float>(gnp);
-      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(N), 0, gnp.bytes - groupnorm_sync_offset(N)));
+      // The GroupNorm kernel's per-image counters must be zero when a forward starts.  Every launch leaves them
+      // zeroed, but a plan can be parked while its workspace is reused by the caller (or a launch can have been
+      // aborted), so they are cleared on the caller's stream at the head of every forward (a few hundred bytes).
+      {
+        uint8_t* sync_ptr = c.base + gnp.off + groupnorm_sync_offset(N);
+        const size_t sync_bytes = gnp.bytes - groupnorm_sync_offset(N);
+        Op op;
+        op.cls = CLS_OTHER;
+        op.launches = 0;
+        op.flops = 0;
+        op.bytes = static_cast<double>(sync_bytes);
+        op.run = [=](cudaStream_t s) { return cudaMemsetAsync(sync_ptr, 0, sync_bytes, s); };
+        c.ops->push_back(op);
+      }
     }
     const size_t M0 = static_cast<size_t>(N) * H * W;
     Buf a0 = c.alloc(M0, kpad_in, 2);
@@ -740,7 +753,20 @@ struct Vae {
     gnp.valid = true;
     if (!c.dry) {
       c.gn_partial = c.ptr<float>(gnp);
-      CUDA_OK(cudaMemset(c.base + gnp.off + groupnorm_sync_offset(N), 0, gnp.bytes - groupnorm_sync_offset(N)));
+      // The GroupNorm kernel's per-image counters must be zero when a forward starts.  Every launch leaves them
+      // zeroed, but a plan can be parked while its workspace is reused by the caller (or a launch can have been
+      // aborted), so they are cleared on the caller's stream at the head of every forward (a few hundred bytes).
+      {
+        uint8_t* sync_ptr = c.base + gnp.off + groupnorm_sync_offset(N);
+        const size_t sync_bytes = gnp.bytes - groupnorm_sync_offset(N);
+        Op op;
+        op.cls = CLS_OTHER;
+        op.launches = 0;
+        op.flops = 0;
+        op.bytes = static_cast<double>(sync_bytes);
+        op.run = [=](cudaStream_t s) { return cudaMemsetAsync(sync_ptr, 0, sync_bytes, s); };
+        c.ops->push_back(op);
+      }
     }
     const size_t M0 = static_cast<size_t>(N) * H * W;
     Buf a0 = c.alloc(M0, kpad_in, 2);
