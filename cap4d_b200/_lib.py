@@ -51,6 +51,7 @@ SIGNATURES = {
     "cap4d_b200_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "cap4d_b200_unet_finalize": (c_int, [c_void_p]),
     "cap4d_b200_unet_set_ref_views": (c_int, [c_void_p, c_int]),
+    "cap4d_b200_unet_ref_view_violations": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_vae_create": (c_int, [POINTER(VaeConfig), POINTER(c_void_p)]),
     "cap4d_b200_vae_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
     "cap4d_b200_vae_num_params": (c_int, [c_void_p, POINTER(c_int)]),

@@ -19,6 +19,7 @@
 //   tile as an MN-major B operand).  O_X accumulates in TMEM over all KV tiles and is rescaled lazily
 //   (only when a row max grows by more than 2^8), so the steady-state softmax is: load S, max (exchanged
 //   between the row's two threads through shared memory), 64 exp2 per thread, pack, store P.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -458,13 +459,17 @@ bool make_attn_plan(AttnPlan* plan, const bf16* qkv, bf16* out, int M, int C, in
 }
 
 cudaError_t launch_attn(const AttnPlan& plan, cudaStream_t stream, long long* trace) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per device: one flag per device ordinal
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool known = dev >= 0 && dev < 64;
+  if (!known || !attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (known) attr_set[dev].store(true, std::memory_order_release);
   }
   AttnParams p;
   p.C = plan.C;

@@ -46,7 +46,8 @@ __global__ void input_pack_kernel(const float* __restrict__ x, const float* __re
 // reference views' outputs do not depend on h at all (ref_mask == 1 there).
 __global__ void output_mix_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ x,
                                   const float* __restrict__ z, const float* __restrict__ mask, int n_img, int cout,
-                                  int H, int W, int G, int V, int R, float* __restrict__ out) {
+                                  int H, int W, int G, int V, int R, float* __restrict__ out,
+                                  int* __restrict__ violations) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -59,7 +60,14 @@ __global__ void output_mix_kernel(const float* __restrict__ h, int ldh, const fl
       hv = h[(n * H * W + sp) * ldh + c];
     } else {
       const int b = static_cast<int>(n) / V, v = static_cast<int>(n) % V;
-      if (v >= R) hv = h[((static_cast<size_t>(b) * G + (v - R)) * H * W + sp) * ldh + c];
+      if (v >= R) {
+        hv = h[((static_cast<size_t>(b) * G + (v - R)) * H * W + sp) * ldh + c];
+      } else if (m == 0.f) {
+        // the caller promised ref_mask == 1 on the first R views (cap4d_b200_unet_set_ref_views) and the network
+        // never computed this view: fail loudly (NaN in the output, counted for ..._ref_view_violations)
+        hv = __int_as_float(0x7fc00000);
+        if (violations != nullptr && c == 0 && sp == 0) atomicAdd(violations, 1);
+      }
     }
     out[i] = (x[i] - z[i]) * m + hv * (m == 0.f ? 1.f : 0.f);
   }
@@ -410,10 +418,10 @@ cudaError_t launch_input_pack(const float* x, const float* z_input, const float*
 
 cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
                               int n_img, int cout, int H, int W, int G, int V, int R, float* out,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int* violations) {
   const size_t total = static_cast<size_t>(n_img) * cout * H * W;
   output_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(h, ldh, x, z_input, ref_mask, n_img, cout, H, W, G, V, R,
-                                                              out);
+                                                              out, violations);
   return cudaGetLastError();
 }
 

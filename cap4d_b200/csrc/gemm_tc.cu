@@ -19,6 +19,7 @@
 // two TMEM accumulator stages when they fit (msub*BN <= 256) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1036,15 +1037,20 @@ static bool residual_lookahead(const GemmParams& p) {
 }
 
 cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per device: one flag per device ordinal (several executors of one process may sit on
+  // different GPUs, e.g. the reference's device_model_map)
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool known = dev >= 0 && dev < 64;
+  if (!known || !attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (known) attr_set[dev].store(true, std::memory_order_release);
   }
   if (plan.two_cta)
     gemm_tc_2sm_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);

@@ -147,7 +147,9 @@ cudaError_t launch_input_pack(const float* x, const float* z_input, const float*
 // Output stage (mmdm_unet.py:118-125): eps = x_input*mask + h*(1-mask), NHWC(ld) -> [n_img][cout][H][W]
 cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
                               int n_img, int cout, int H, int W, int G, int V, int R, float* out,
-                              cudaStream_t stream);
+                              cudaStream_t stream, int* violations = nullptr);
+// violations: device counter, incremented once per view that was declared a reference view (v < R with G > 0)
+// but has ref_mask == 0 somewhere at its first pixel row; such views come out as NaN.
 // dst image (b, g) = src image (b, R + g) for g < V - R: drops the R leading (reference) views of every group
 cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int R, size_t per_img, cudaStream_t stream);
 // fp32 NHWC -> bf16 parity planes [4][n_img][H/2][W/2][C] (plane = (y&1)*2 + (x&1))

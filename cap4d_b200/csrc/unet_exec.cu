@@ -107,6 +107,7 @@ struct Unet {
   // Caller's promise (cap4d_b200_unet_set_ref_views): the first ref_views views of every group are reference
   // views (ref_mask == 1), so their outputs are x - z_input whatever the network computes for them.
   int ref_views = 0;
+  int* d_violations = nullptr;  // broken n_ref_views promises seen by the output mix (device counter)
   void* p_ws = nullptr;
   size_t p_ws_bytes = 0;
   struct CachedPlan {
@@ -495,6 +496,7 @@ struct Unet {
       if (!get("out.2.bias", cfg.out_channels, &t)) return false;
       CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice));
     }
+    d_violations = dev_alloc<int>(1, true);
     CUDA_OK(cudaDeviceSynchronize());
     // the big fp32 originals are no longer needed
     for (const std::string& name : consumed) {
@@ -829,6 +831,14 @@ struct Unet {
       set_error("n_ref_views must be in [0, V)");
       return false;
     }
+    // the "3d" transformers regroup '(b t) n c -> b (t n) c' with t = time_steps (attention.py:233): with another
+    // V the reference attends over different token sets than one sequence per group
+    for (const TfW& w : tf)
+      if (w.is3d && V != cfg.time_steps) {
+        set_error("V = " + std::to_string(V) + " views per group, but the model's cross-view attention was built for "
+                  "time_steps = " + std::to_string(cfg.time_steps));
+        return false;
+      }
     if (R > 0 && last_3d_in_up_path(&cb, &cl)) {
       c.R = R;
       c.G = V - R;
@@ -971,13 +981,14 @@ struct Unet {
       const float* po = c.ptr<float>(o32);
       const int cout = cfg.out_channels;
       const int mixG = c.compact ? c.G : 0, mixR = c.R;
+      int* viol = d_violations;
       Op op;
       op.cls = CLS_OTHER;
       op.launches = 1;
       op.flops = 0;
       op.bytes = static_cast<double>(M0) * cout * 16;
       op.run = [=](cudaStream_t s) {
-        return launch_output_mix(po, 32, iop->x, iop->z, iop->mask, n_img, cout, H, W, mixG, V, mixR, iop->out, s);
+        return launch_output_mix(po, 32, iop->x, iop->z, iop->mask, n_img, cout, H, W, mixG, V, mixR, iop->out, s, viol);
       };
       c.ops->push_back(op);
     }
@@ -1266,6 +1277,24 @@ int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views) {
     return 1;
   }
   u->ref_views = n_ref_views;
+  return 0;
+}
+
+int cap4d_b200_unet_ref_view_violations(void* handle, int* n) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *n = 0;
+  if (u->d_violations == nullptr) return 0;
+  // blocking read on the legacy default stream: it waits for the caller's (blocking) streams
+  cudaError_t e = cudaMemcpy(n, u->d_violations, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(u->d_violations, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    return 6;
+  }
   return 0;
 }
 

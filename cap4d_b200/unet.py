@@ -62,29 +62,66 @@ def config_from_reference(ref_unet) -> Dict:
 class B200MMDMUnet(torch.nn.Module):
     """Drop-in for MMDMUnetModel on one B200.  Weights are uploaded and repacked once."""
 
-    def __init__(self, config: Mapping, state_dict: Mapping[str, torch.Tensor], device: Optional[torch.device] = None):
+    def __init__(self, config: Mapping, state_dict: Mapping[str, torch.Tensor], device: Optional[torch.device] = None,
+                 keep_state: bool = False, lazy: bool = False):
+        """keep_state: keep references (no copies) to the fp32 `state_dict` tensors, which is what lets the module
+        be deep-copied and moved to another GPU like the reference's nn.Module (generate_images.py:62-71:
+        `copy.deepcopy(model).to(f"cuda:{i}")`).  lazy: upload / repack the weights at the first forward or
+        `.to(device)` instead of now (implies keep_state)."""
         super().__init__()
         if not torch.cuda.is_available():
             raise RuntimeError("cap4d_b200: a CUDA device (B200, sm_100a) is required; there is no CPU path")
         self.config = dict(config)
         self._device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self._device.type != "cuda":
+            raise RuntimeError("cap4d_b200: a CUDA device (B200, sm_100a) is required; there is no CPU path")
+        if self._device.index is None:
+            self._device = torch.device(f"cuda:{torch.cuda.current_device()}")
         self._lib = _lib.load()
         self._handle = ctypes.c_void_p()
-        self._ws: Dict = {}  # (B, V, H, W) -> workspace tensor (a launch plan is bound to its workspace)
+        self._ws: Dict = {}  # (B, V, H, W, R) -> workspace tensor (a launch plan is bound to its workspace)
         self.dtype = torch.float32
         self.time_steps = int(config["time_steps"])
-        cfg = _make_config(config)
+        _make_config(config)  # validate now, even when lazy
+        self._state = dict(state_dict) if (keep_state or lazy) else None
+        if not lazy:
+            self._build(state_dict)
+
+    def _build(self, state_dict: Mapping[str, torch.Tensor]) -> None:
+        """Create the library handle on self._device: upload every tensor, repack (finalize)."""
+        self._release()
+        cfg = _make_config(self.config)
+        handle = ctypes.c_void_p()
         with torch.cuda.device(self._device):
-            _lib.check(self._lib.cap4d_b200_unet_create(ctypes.byref(cfg), ctypes.byref(self._handle)), "unet_create")
-            for name, t in state_dict.items():
-                t32 = t.detach().to(dtype=torch.float32).contiguous()
-                shape = (ctypes.c_int64 * max(1, t32.dim()))(*t32.shape)
-                _lib.check(
-                    self._lib.cap4d_b200_unet_load_weight(self._handle, name.encode(), ctypes.c_void_p(t32.data_ptr()),
-                                                          shape, t32.dim()),
-                    f"load_weight({name})",
-                )
-            _lib.check(self._lib.cap4d_b200_unet_finalize(self._handle), "unet_finalize")
+            _lib.check(self._lib.cap4d_b200_unet_create(ctypes.byref(cfg), ctypes.byref(handle)), "unet_create")
+            try:
+                for name, t in state_dict.items():
+                    t32 = t.detach().to(dtype=torch.float32).contiguous()
+                    shape = (ctypes.c_int64 * max(1, t32.dim()))(*t32.shape)
+                    _lib.check(
+                        self._lib.cap4d_b200_unet_load_weight(handle, name.encode(), ctypes.c_void_p(t32.data_ptr()),
+                                                              shape, t32.dim()),
+                        f"load_weight({name})",
+                    )
+                _lib.check(self._lib.cap4d_b200_unet_finalize(handle), "unet_finalize")
+            except Exception:
+                self._lib.cap4d_b200_unet_destroy(handle)
+                raise
+        self._handle = handle
+
+    def _release(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            with torch.cuda.device(self._device):
+                torch.cuda.synchronize(self._device)
+                self._lib.cap4d_b200_unet_destroy(self._handle)
+        self._handle = ctypes.c_void_p()
+        self._ws = {}
+
+    def _ensure_built(self) -> None:
+        if not self._handle.value:
+            if self._state is None:
+                raise RuntimeError("B200MMDMUnet has no weights to build from")
+            self._build(self._state)
 
     @staticmethod
     def param_shapes(config: Mapping) -> Dict[str, tuple]:
@@ -135,13 +172,50 @@ class B200MMDMUnet(torch.nn.Module):
         return cls(config, sd, device=dev)
 
     @classmethod
-    def from_reference(cls, ref_unet, device=None) -> "B200MMDMUnet":
-        return cls(config_from_reference(ref_unet), ref_unet.state_dict(), device=device)
+    def from_reference(cls, ref_unet, device=None, lazy: bool = False) -> "B200MMDMUnet":
+        """Built from a constructed reference MMDMUnetModel; keeps references to its fp32 tensors so that the
+        result can be deep-copied / moved between GPUs like the module it replaces."""
+        sd = {k: v.detach() for k, v in ref_unet.state_dict().items()}
+        return cls(config_from_reference(ref_unet), sd, device=device, keep_state=True, lazy=lazy)
 
-    # the reference moves/copies whole models around (generate_images.py:62-71); this module is bound
-    # to the device it was built on
+    # The reference copies and moves whole models (generate_images.py:62-71: copy.deepcopy(model).to("cuda:i")).
+    # The device state of this module lives behind the library handle, so a copy shares the fp32 source tensors
+    # (by reference) and builds its own handle where it lands: at `.to(device)` or at its first forward.
     def __deepcopy__(self, memo):
-        raise RuntimeError("B200MMDMUnet is bound to one GPU: build one instance per device instead of deepcopy")
+        if self._state is None:
+            raise RuntimeError("this B200MMDMUnet was built without keep_state=True (e.g. random_init): it does not "
+                               "hold its fp32 weights and cannot be copied; build one instance per device instead")
+        new = B200MMDMUnet.__new__(B200MMDMUnet)
+        torch.nn.Module.__init__(new)
+        new.config = dict(self.config)
+        new._device = self._device
+        new._lib = self._lib
+        new._handle = ctypes.c_void_p()
+        new._ws = {}
+        new.dtype = self.dtype
+        new.time_steps = self.time_steps
+        new._state = self._state
+        new.record_every = self.record_every
+        memo[id(self)] = new
+        return new
+
+    def _apply(self, fn, recurse=True):
+        """nn.Module.to / .cuda / .float land here.  Only the device matters (the arithmetic types are fixed);
+        moving to another GPU rebuilds the handle there from the kept fp32 weights."""
+        probe = fn(torch.empty(0, dtype=torch.float32, device=self._device))
+        target = probe.device
+        if target.type != "cuda":
+            raise RuntimeError("cap4d_b200: there is no CPU path; B200MMDMUnet cannot be moved off the GPU")
+        if target.index is None:
+            target = torch.device(f"cuda:{torch.cuda.current_device()}")
+        if target != self._device:
+            if self._state is None:
+                raise RuntimeError("this B200MMDMUnet was built without keep_state=True and cannot change device")
+            self._release()
+            self._device = target
+        if self._state is not None:
+            self._ensure_built()
+        return self
 
     @property
     def device(self):
@@ -155,7 +229,17 @@ class B200MMDMUnet(torch.nn.Module):
         except Exception:
             pass
 
+    def check_ref_views(self) -> int:
+        """Number of forwards since the last call whose `n_ref_views` promise was broken (a view declared a
+        reference view had ref_mask != 1; its outputs were poisoned with NaN).  Synchronises the stream."""
+        self._ensure_built()
+        n = ctypes.c_int()
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.cap4d_b200_unet_ref_view_violations(self._handle, ctypes.byref(n)), "ref_view_violations")
+        return n.value
+
     def _workspace(self, B, V, H, W, R=0) -> torch.Tensor:
+        self._ensure_built()
         _lib.check(self._lib.cap4d_b200_unet_set_ref_views(self._handle, int(R)), "set_ref_views")
         key = (B, V, H, W, R)
         ws = self._ws.get(key)
@@ -229,6 +313,7 @@ class B200MMDMUnet(torch.nn.Module):
 
     def collect_timings(self):
         """Per-class ms summed over the recorded forwards since the last call -> ({class: ms}, n_forwards)."""
+        self._ensure_built()
         ms = (ctypes.c_float * _lib.N_CLASSES)()
         n = ctypes.c_int()
         _lib.check(self._lib.cap4d_b200_unet_collect_timings(self._handle, ms, ctypes.byref(n)), "collect_timings")
@@ -254,6 +339,7 @@ class B200MMDMUnet(torch.nn.Module):
 
     def class_stats(self):
         """Algorithmic FLOPs / bytes / launches per kernel class of the current plan."""
+        self._ensure_built()
         fl = (ctypes.c_double * _lib.N_CLASSES)()
         by = (ctypes.c_double * _lib.N_CLASSES)()
         ln = (ctypes.c_int * _lib.N_CLASSES)()
@@ -261,14 +347,19 @@ class B200MMDMUnet(torch.nn.Module):
         return {n: dict(flops=fl[i], bytes=by[i], launches=ln[i]) for i, n in enumerate(_lib.CLASS_NAMES)}
 
     def num_launches(self) -> int:
+        self._ensure_built()
         n = ctypes.c_int()
         _lib.check(self._lib.cap4d_b200_unet_num_launches(self._handle, ctypes.byref(n)), "num_launches")
         return n.value
 
 
-def install(mmldm, device=None) -> B200MMDMUnet:
-    """Replace `mmldm.model.diffusion_model` (ddpm.py:1318) by the B200 implementation, in place."""
+def install(mmldm, device=None, lazy: bool = False) -> B200MMDMUnet:
+    """Replace `mmldm.model.diffusion_model` (ddpm.py:1318) by the B200 implementation, in place.
+
+    lazy=True is the form for the reference's own driver (generate_images.py:59-71): call it right after
+    `load_model(...)` while the model is still on the CPU; every `copy.deepcopy(model).to(f"cuda:{i}")` that
+    follows then uploads and repacks the weights once, on its own GPU."""
     ref_unet = mmldm.model.diffusion_model
-    new = B200MMDMUnet.from_reference(ref_unet, device=device)
+    new = B200MMDMUnet.from_reference(ref_unet, device=device, lazy=lazy)
     mmldm.model.diffusion_model = new
     return new

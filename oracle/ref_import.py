@@ -3,7 +3,7 @@
 The reference needs `omegaconf` and `pytorch_lightning`, neither of which is installed here; the
 hot path uses them only for an isinstance check (openaimodel.py:479-483) and as a base class
 (ddpm.py:12,21 / autoencoder.py:2).  Two stub modules are enough.  /root/reference
-does not exist on the GPU box: nothing that runs there may import this module.
+does not exist on the GPU box; there the verbatim copy under oracle/_ref (oracle/build_ref.py) is imported.
 """
 import os
 import sys
@@ -11,7 +11,19 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("CAP4D_REFERENCE_ROOT", "/root/reference")
+_REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # made by oracle/build_ref.py
+
+
+def _find_root() -> str:
+    """The reference tree itself where it exists (authoring container), else the verbatim copy of its hot-path
+    modules that oracle/build_ref.py placed under oracle/_ref (the GPU box)."""
+    for cand in (os.environ.get("CAP4D_REFERENCE_ROOT"), "/root/reference", _REF_COPY):
+        if cand and os.path.isdir(os.path.join(cand, "cap4d", "mmdm")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -35,12 +47,32 @@ def install_stubs() -> None:
         pl = types.ModuleType("pytorch_lightning")
 
         class LightningModule(torch.nn.Module):
+            # Lightning's DeviceDtypeModuleMixin: `.device` is what the last .to() / .cuda() / .cpu() set
+            _stub_device = None
+
             @property
             def device(self):
+                if self._stub_device is not None:
+                    return self._stub_device
                 try:
                     return next(self.parameters()).device
                 except StopIteration:
                     return torch.device("cpu")
+
+            def to(self, *args, **kwargs):
+                device = torch._C._nn._parse_to(*args, **kwargs)[0]
+                if device is not None:
+                    self._stub_device = torch.device(device)
+                return super().to(*args, **kwargs)
+
+            def cuda(self, device=None):
+                self._stub_device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                                 torch.device(device).index if not isinstance(device, int) else device)
+                return super().cuda(device)
+
+            def cpu(self):
+                self._stub_device = torch.device("cpu")
+                return super().cpu()
 
             def log(self, *a, **k):
                 pass

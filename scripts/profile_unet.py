@@ -29,8 +29,8 @@ def main():
     args = ap.parse_args()
     R = args.ref_views
     dev = torch.device("cuda:0")
-    unet = B200MMDMUnet.random_init(MMDM_UNET_CONFIG, seed=0, device=dev)
     B, V, H = 2 * args.groups, args.views, args.hw
+    unet = B200MMDMUnet.random_init(dict(MMDM_UNET_CONFIG, time_steps=V), seed=0, device=dev)
     g = torch.Generator(device=dev).manual_seed(1)
     x = torch.randn(B, V, 4, H, H, generator=g, device=dev)
     ctrl = dict(z_input=torch.randn(B, V, 4, H, H, generator=g, device=dev),

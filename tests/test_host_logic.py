@@ -342,3 +342,23 @@ def test_vae_encoder_param_shapes_match_oracle():
 
     for cfg in (VO.TINY_VAE, VO.PRODUCTION_VAE):
         assert B200VAEDecoder.encoder_param_shapes(cfg) == dict(VO.vae_encoder_param_shapes(cfg))
+
+
+def test_config_from_reference_matches_the_real_module():
+    """config_from_reference / param_shapes against a constructed reference MMDMUnetModel (the unmodified module,
+    from /root/reference or its verbatim copy under oracle/_ref): same hyper-parameters back, same state_dict keys
+    and shapes - what install() relies on."""
+    from oracle import mmdm_oracle as O
+    from oracle import ref_import as RI
+
+    if not RI.reference_available():
+        pytest.skip("reference modules not available (run oracle/build_ref.py)")
+    from cap4d_b200 import B200MMDMUnet
+    from cap4d_b200.unet import config_from_reference
+
+    ref = RI.build_reference_unet(O.TINY_CONFIG)
+    cfg = config_from_reference(ref)
+    assert cfg == {k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in O.TINY_CONFIG.items()}
+    want = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    got = B200MMDMUnet.param_shapes(cfg)
+    assert got == want and len(got) > 100
