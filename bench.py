@@ -4,7 +4,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference ...        # the reference's own U-Net on the host cores (oracle/_ref; else the port)
 
 Workload (config.workload): configs/generation/single_ref.yaml - 1 reference view, 840 generated
 views in groups of V = 8 (1 + 7), CFG 2.0, 64x64x4 latents (512^2 images), the shipped
@@ -115,38 +115,90 @@ def synthetic_conditioning(n_ref, n_gen, seed, pin):
 
 
 # =============================================================================================
-# reference arm / CPU baseline: the reference algorithm (oracle port) on the host cores
+# reference arm / CPU baseline: the reference's own U-Net on the host cores
 # =============================================================================================
-def cpu_unet_seconds(n_timed, n_warm, budget_s):
-    """Times the oracle U-Net (fp32, torch CPU, all host threads) on ONE conditional half-batch of the
-    production group shape (B=1, V=8, 64x64): the CFG pair of a group is two such identical halves."""
+def workload_config(workload, n_gen, n_all_ref, G, gpc, calls_per_step, world, graphs):
+    """`config` of the JSON line - the SAME dict for the B200 arm and the reference arm (the reference arm times a
+    bounded sample of this workload, which its cpu_baseline.sample says)."""
+    return {
+        "workload": f"{workload}.yaml: {V - G} ref + {G} gen views per group (V=8"
+                    f"{', 4 of 10 references drawn per group and step' if n_all_ref > 1 else ''}), 64x64 latents, "
+                    "cap4d_mmdm_final U-Net (815.5M params), random-init",
+        "n_gen": n_gen, "S": S_TOTAL, "cfg_scale": CFG_SCALE, "groups_per_call": gpc,
+        "unet_calls_per_step_per_rank": calls_per_step,
+        "parallelism": f"view-groups sharded over {world} rank(s), 1 all-gather of latents per step",
+        "l2": "working set per step (1.6 GB weights + GBs of activations) >> 126 MB L2; no explicit flush",
+        "step": "one DDIM step over all n_gen views; value = n_gen / (S * s_per_step)",
+        "cuda_graph": graphs,
+    }
+
+
+def _shape_args(args, world):
+    n_all_ref = 1 if args.workload == "single_ref" else 10     # multi_ref.yaml: n_all_ref 10, R_max 4
+    G = V - min(n_all_ref, 4)                                   # generated views per group
+    assert args.n_gen % G == 0
+    groups_per_rank = (args.n_gen // G + world - 1) // world
+    # every U-Net call of the timed region has the same batch shape: pick a divisor of the rank's share
+    gpc = max(d for d in range(1, max(1, args.groups_per_call) + 1) if groups_per_rank % d == 0)
+    return n_all_ref, G, groups_per_rank, gpc
+
+
+def _cpu_forward_fn(R):
+    """One forward of the production U-Net on a conditional half-batch (B=1, V=8, 64x64), fp32, torch CPU with all
+    host threads: the UNMODIFIED reference module when oracle/_ref (or /root/reference) is importable ("reference"),
+    else the oracle's restatement ("port")."""
     from oracle import mmdm_oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = O.PRODUCTION_CONFIG
     sd = O.init_state_dict(cfg, seed=0)
-    x, t, ctrl = O.make_inputs(cfg, B=1, V=8, H=64, W=64, R=1, seed=1)
+    x, t, ctrl = O.make_inputs(cfg, B=1, V=8, H=64, W=64, R=R, seed=1)
+    try:
+        from oracle import ref_import as RI
+
+        if not RI.reference_available():
+            raise RuntimeError("no reference copy")
+        ref = RI.build_reference_unet(cfg)
+        ref.load_state_dict(sd)
+        del sd
+
+        def fwd():
+            with torch.no_grad():
+                return ref(x, timesteps=t, context=None, control=ctrl)
+
+        return fwd, "reference"
+    except Exception as e:  # the reference copy is missing or does not import here
+        print(f"bench: reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return (lambda: O.unet_forward(sd, cfg, x, t, ctrl)), "port"
+
+
+def cpu_unet_seconds(n_timed, n_warm, budget_s, R=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fwd, kind = _cpu_forward_fn(R)
     times = []
     t_start = time.time()
     for i in range(n_warm + n_timed):
         t0 = time.time()
-        O.unet_forward(sd, cfg, x, t, ctrl)
+        fwd()
         dt = time.time() - t0
         if i >= n_warm:
             times.append(dt)
         if time.time() - t_start > budget_s and times:
             break
-    return times, cores
+    return times, cores, kind
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     if rank != 0:
         return
-    times, cores = cpu_unet_seconds(max(1, args.steps), min(args.warmup, 1), budget_s=240.0)
+    n_all_ref, G, groups_per_rank, gpc = _shape_args(args, world)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    # every step is one forward of the sample (8-30 s on the box's cores): all W warm-ups and K steps are run unless
+    # the run would exceed ~10 minutes, in which case the remaining steps are dropped and `steps` says so
+    times, cores, kind = cpu_unet_seconds(K, W, budget_s=600.0, R=min(n_all_ref, 4))
     t_half = float(np.median(times))
-    # one group = 2 halves -> 7 generated views advance one DDIM step; a view needs S_TOTAL steps
-    views_per_s = 7.0 / (2.0 * t_half * S_TOTAL)
+    # one group = 2 halves -> G generated views advance one DDIM step; a view needs S_TOTAL steps
+    views_per_s = float(G) / (2.0 * t_half * S_TOTAL)
     line = {
         "impl": "reference",
         "metric": "generated_views_per_sec",
@@ -154,17 +206,18 @@ def run_reference(args, rank):
         "unit": "views/s (512^2, 100 DDIM steps, cfg 2.0)",
         "n_gpus": args.gpus,
         "steps": len(times),
-        "warmup": min(args.warmup, 1),
-        "ms_per_step": t_half * 1e3,
+        "warmup": W,
+        "ms_per_step": t_half * 1e3 * 2 * (args.n_gen // G),   # a DDIM step over all views = 2 halves x groups
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "single_ref.yaml: 1 ref + 7 gen views per group (V=8), 64x64 latents, "
-                               "cap4d_mmdm_final U-Net, random-init", "n_gen": args.n_gen, "S": S_TOTAL},
-        "cpu_baseline": {"value": views_per_s, "unit": "views/s", "cores": cores, "kind": "port",
-                         "sample": "one U-Net forward of a conditional half-batch (B=1, V=8, 64x64) per step; "
+        "config": workload_config(args.workload, args.n_gen, n_all_ref, G, gpc, groups_per_rank // gpc, world,
+                                  not args.no_cuda_graph),
+        "cpu_baseline": {"value": views_per_s, "unit": "views/s", "cores": cores, "kind": kind,
+                         "sample": f"per step ONE forward of the {'unmodified reference MMDMUnetModel' if kind == 'reference' else 'oracle port'} "
+                                   f"on a conditional half-batch (B=1, V=8, 64x64, fp32): median {t_half:.1f} s; "
                                    "a group's CFG pair = 2 such halves; extrapolated linearly in groups x steps"},
         "e2e": {"value": views_per_s, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -172,19 +225,100 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def gpu_eager_baseline(dev, G, R):
+    """Stock PyTorch on the same GPU: one U-Net call on a group's CFG pair
+    (B=2, V=8, 64x64), eager, no custom kernel - the number the hand-written path must beat.
+      reference_fp32       the unmodified reference module, fp32, TF32 off (its shipped precision)
+      reference_bf16       the same module under torch.autocast(bfloat16) (materialised-softmax attention)
+      port_bf16_sdpa       the oracle's functional restatement under autocast with F.scaled_dot_product_attention"""
+    from oracle import mmdm_oracle as O
+
+    out = {"shape": "B=2 (CFG pair of one group), V=8, 64x64", "unit": "views/s (100 DDIM steps)"}
+    cfg = O.PRODUCTION_CONFIG
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(cfg, seed=0).items()}
+    x, t, ctrl = O.make_inputs(cfg, B=2, V=8, H=64, W=64, R=R, seed=1)
+    x, t = x.to(dev), t.to(dev)
+    ctrl = {k: v.to(dev) for k, v in ctrl.items()}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def timed(fn, iters):
+        with torch.no_grad():
+            fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        return {"ms_per_unet_call": ms, "value": G / (S_TOTAL * ms * 1e-3)}
+
+    try:
+        ref = None
+        try:
+            from oracle import ref_import as RI
+
+            if RI.reference_available():
+                ref = RI.build_reference_unet(cfg)
+                ref.load_state_dict({k: v.cpu() for k, v in sd.items()})
+                ref = ref.to(dev)
+        except Exception as e:
+            out["reference_error"] = f"{type(e).__name__}: {e}"
+            ref = None
+        if ref is not None:
+            out["reference_fp32"] = timed(lambda: ref(x, timesteps=t, context=None, control=ctrl), 2)
+
+            def ref_bf16():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return ref(x, timesteps=t, context=None, control=ctrl)
+
+            out["reference_bf16_autocast"] = timed(ref_bf16, 3)
+            del ref
+        else:
+            out["port_fp32"] = timed(lambda: O.unet_forward(sd, cfg, x, t, ctrl), 2)
+        O.ATTENTION_IMPL = "sdpa"
+
+        def port_bf16():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.unet_forward(sd, cfg, x, t, ctrl)
+
+        out["port_bf16_autocast_sdpa"] = timed(port_bf16, 3)
+    except Exception as e:  # a baseline must never take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"
+    finally:
+        O.ATTENTION_IMPL = "legacy"
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+    return out
+
+
 # =============================================================================================
 # B200 arm
 # =============================================================================================
-def _gemm_traffic(gpc):
-    """DRAM bytes per gemm_tc_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
-    launches of one U-Net call) from the committed ncu capture of the same batch shape; None if there is none."""
-    path = os.path.join(ROOT, "profiles", f"r01d_traffic_g{gpc}.json")
+def _gemm_traffic(gpc, workload):
+    """DRAM bytes per gemm_tc_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the GEMM
+    launches) from the ncu pass over THIS script (scripts/ncu_bench_traffic.sh -> profiles/r02_traffic_bench.json).
+    The file carries the digest of the kernel sources it was captured with; a capture of other sources, another
+    batch shape or another workload is refused (traffic = null) instead of being reported as current."""
+    from cap4d_b200 import build as _build
+
+    path = os.path.join(ROOT, "profiles", "r02_traffic_bench.json")
     try:
         with open(path) as f:
-            k = json.load(f)["kernels"]["gemm_tc_kernel"]
-        return k["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+            d = json.load(f)
     except Exception:
-        return None, None
+        return None, "no ncu capture of bench.py (scripts/ncu_bench_traffic.sh)"
+    if d.get("source_digest") != _build._digest():
+        return None, f"{os.path.relpath(path, ROOT)} is stale: captured with other kernel sources"
+    if d.get("groups_per_call") != gpc or d.get("workload") != workload:
+        return None, f"{os.path.relpath(path, ROOT)} was captured for another batch shape / workload"
+    try:
+        return d["kernels"]["gemm_tc_kernel"]["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+    except Exception:
+        return None, f"{os.path.relpath(path, ROOT)} holds no gemm_tc_kernel entry"
 
 
 def main():
@@ -200,6 +334,9 @@ def main():
     ap.add_argument("--groups-per-call", type=int, default=5,
                     help="upper bound; the largest divisor of the groups per rank not above it is used")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="launch every kernel from the host instead of replaying the captured call graphs (ncu passes)")
     ap.add_argument("--record-every", type=int, default=4, help="record per-launch events on every n-th U-Net call")
     args = ap.parse_args()
 
@@ -208,7 +345,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch.distributed as dist
@@ -224,12 +361,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), max(1, args.steps)
     n_gen = args.n_gen
-    n_all_ref = 1 if args.workload == "single_ref" else 10     # multi_ref.yaml: n_all_ref 10, R_max 4
-    G = V - min(n_all_ref, 4)                                   # generated views per group
-    assert n_gen % G == 0
-    groups_per_rank = (n_gen // G + world - 1) // world
-    # every U-Net call of the timed region has the same batch shape: pick a divisor of the rank's share
-    gpc = max(d for d in range(1, max(1, args.groups_per_call) + 1) if groups_per_rank % d == 0)
+    n_all_ref, G, groups_per_rank, gpc = _shape_args(args, world)
+    graphs = not args.no_cuda_graph
 
     unet = B200MMDMUnet.random_init(MMDM_UNET_CONFIG, seed=0, device=dev)
     model = B200MMLDM(unet)
@@ -243,7 +376,7 @@ def main():
     # ---------------- device-resident steady state: W warm-up + K timed DDIM steps ----------------
     torch.manual_seed(124)
     np.random.seed(124)
-    sampler = B200StochasticIOSampler(model, groups_per_call=gpc)
+    sampler = B200StochasticIOSampler(model, groups_per_call=gpc, use_cuda_graph=graphs)
     st = sampler.begin(S_TOTAL, rc, ru, gc, gu, LATENT, V=V, R_max=4, cfg_scale=CFG_SCALE)
     for _ in range(W):
         sampler.step(st)
@@ -277,7 +410,7 @@ def main():
     # ---------------- end to end through the public API from host tensors ----------------
     torch.manual_seed(124)
     np.random.seed(124)
-    s2 = B200StochasticIOSampler(model, groups_per_call=gpc)
+    s2 = B200StochasticIOSampler(model, groups_per_call=gpc, use_cuda_graph=graphs)
     barrier()
     t0 = time.perf_counter()
     st2 = s2.begin(S_TOTAL, rc, ru, gc, gu, LATENT, V=V, R_max=4, cfg_scale=CFG_SCALE)   # H2D of everything
@@ -297,7 +430,10 @@ def main():
         peaks = _peaks()
         gemm_ms = class_ms["conv3x3"] + class_ms["linear"]
         gemm_flops = (stats["conv3x3"]["flops"] + stats["linear"]["flops"]) * n_rec
+        gemm_exec = (stats["conv3x3"]["exec_flops"] + stats["linear"]["exec_flops"]) * n_rec
         achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        executed_tf = gemm_exec / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        traffic, traffic_src = _gemm_traffic(gpc, args.workload)
         total_rec_ms = sum(class_ms.values())
         kernels = {}
         for c, ms in class_ms.items():
@@ -307,6 +443,9 @@ def main():
             if stats[c]["flops"] > 0 and c != "other":
                 k["tflops"] = stats[c]["flops"] * n_rec / (ms * 1e-3) / 1e12
                 k["frac_of_bf16_peak"] = k["tflops"] / peaks["tf_sustained"]
+                k["algorithmic_flops_per_call"] = stats[c]["flops"]
+                k["executed_flops_per_call"] = stats[c]["exec_flops"]
+                k["executed_tflops"] = stats[c]["exec_flops"] * n_rec / (ms * 1e-3) / 1e12
             if stats[c]["bytes"] > 0:
                 k["gbs"] = stats[c]["bytes"] * n_rec / (ms * 1e-3) / 1e9
                 k["frac_of_hbm_peak"] = k["gbs"] / peaks["hbm_gbs"]
@@ -325,16 +464,7 @@ def main():
             "vs_baseline": None,
             "dtype": "bf16",
             "data": "synthetic",
-            "config": {
-                "workload": f"{args.workload}.yaml: {V - G} ref + {G} gen views per group (V=8"
-                            f"{', 4 of 10 references drawn per group and step' if n_all_ref > 1 else ''}), 64x64 latents, "
-                            "cap4d_mmdm_final U-Net (815.5M params), random-init",
-                "n_gen": n_gen, "S": S_TOTAL, "cfg_scale": CFG_SCALE, "groups_per_call": gpc,
-                "unet_calls_per_step_per_rank": calls_timed // K,
-                "parallelism": f"view-groups sharded over {world} rank(s), 1 all-gather of latents per step",
-                "l2": "working set per step (1.6 GB weights + GBs of activations) >> 126 MB L2; no explicit flush",
-                "step": "one DDIM step over all n_gen views; value = n_gen / (S * s_per_step)",
-            },
+            "config": workload_config(args.workload, n_gen, n_all_ref, G, gpc, calls_timed // K, world, graphs),
             "unet_step_ms": unet_ms,
             # executed FLOPs of the plan (the sampler's calls drop the reference view after the last cross-view
             # layer: ~3 % fewer FLOPs than the reference's 14.034 TFLOP per group, same outputs)
@@ -344,11 +474,15 @@ def main():
             "roofline": {
                 "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": _gemm_traffic(gpc)[0],
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
-                                "GEMM launches of one U-Net call)", "traffic_source": _gemm_traffic(gpc)[1],
+                                "GEMM launches of this script's U-Net calls)", "traffic_source": traffic_src,
+                "executed": executed_tf, "executed_frac": executed_tf / peaks["tf_sustained"],
+                "executed_note": "achieved / frac count ALGORITHMIC FLOPs (the reference op); executed counts what the "
+                                 "tensor core runs (the folded upsample convs execute 4/9 of their algorithmic FLOPs)",
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "how": f"CUDA events around every launch of {n_rec} of {calls_timed} U-Net calls inside the timed region",
+                "how": f"CUDA events around every launch of {n_rec} of {calls_timed} U-Net calls inside the timed region "
+                       "(those calls are launched from the host, the others replay the captured call graph)",
             },
             "kernels": kernels,
             "clocks": clock_info,
@@ -357,14 +491,20 @@ def main():
                     "seconds": e2e_s, "steps": K, "checksum": checksum,
                     "note": "begin() uploads ALL conditioning + x_T once and end() downloads the latents; "
                             "amortised here over K steps instead of the production 100"},
-            "gpu_launches": calls_timed * (launches_per_call + 1),
+            "gpu_launches": calls_timed * (launches_per_call + 2),   # + gather + CFG/DDIM update per call
+            "cuda_graphs": {"captured": sampler.backend.graphs_captured, "replays": sampler.backend.graph_replays},
         }
+        if not args.no_gpu_eager_baseline and world == 1:
+            del s2, st2
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, G, min(n_all_ref, 4))
         if not args.no_cpu_baseline and world == 1:
-            times, cores = cpu_unet_seconds(1, 0, budget_s=120.0)
+            times, cores, kind = cpu_unet_seconds(1, 0, budget_s=120.0, R=min(n_all_ref, 4))
             t_half = float(np.median(times))
             line["cpu_baseline"] = {
-                "value": float(G) / (2.0 * t_half * S_TOTAL), "unit": "views/s", "cores": cores, "kind": "port",
-                "sample": f"one oracle U-Net forward of a conditional half-batch (B=1, V=8, 64x64): {t_half:.1f} s; "
+                "value": float(G) / (2.0 * t_half * S_TOTAL), "unit": "views/s", "cores": cores, "kind": kind,
+                "sample": f"one forward of the {'unmodified reference MMDMUnetModel' if kind == 'reference' else 'oracle port'} on a "
+                          f"conditional half-batch (B=1, V=8, 64x64, fp32): {t_half:.1f} s; "
                           "a group's CFG pair = 2 halves; extrapolated linearly in groups x steps",
             }
         print(json.dumps(line), flush=True)

@@ -31,6 +31,20 @@ class UnetConfig(ctypes.Structure):
     ]
 
 
+MAX_GROUPS_PER_CALL = 16
+
+
+class SamplerStores(ctypes.Structure):
+    _fields_ = [(name, c_void_p) for name in (
+        "ref_z", "ref_mask", "ref_pos", "gen_z", "gen_mask", "gen_pos",
+        "ref_z_u", "ref_mask_u", "ref_pos_u", "gen_z_u", "gen_mask_u", "gen_pos_u", "latents")]
+
+
+class SamplerCall(ctypes.Structure):
+    _fields_ = [("timestep", c_int64), ("x_coef", c_float), ("e_coef", c_float), ("n_groups", ctypes.c_int32),
+                ("pad_", ctypes.c_int32), ("groups", ctypes.c_int32 * MAX_GROUPS_PER_CALL)]
+
+
 class VaeConfig(ctypes.Structure):
     _fields_ = [
         ("ch", c_int),
@@ -75,6 +89,7 @@ SIGNATURES = {
     ),
     "cap4d_b200_unet_num_launches": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_unet_class_stats": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int)]),
+    "cap4d_b200_unet_class_exec_flops": (c_int, [c_void_p, POINTER(c_double)]),
     "cap4d_b200_unet_forward_timed": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
@@ -84,6 +99,13 @@ SIGNATURES = {
     "cap4d_b200_unet_destroy": (c_int, [c_void_p]),
     "cap4d_b200_cfg_ddim_update": (
         c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "cap4d_b200_sampler_gather": (
+        c_int, [POINTER(SamplerStores), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cap4d_b200_sampler_update": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "cap4d_b200_sampler_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cap4d_b200_sampler_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cap4d_b200_gemm_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                 POINTER(c_float), c_int]),

@@ -100,25 +100,6 @@ __device__ __forceinline__ float ex2f(float x) {
 #endif
 }
 
-// A/B builds only (CAP4D_ATTN_POLY_EVERY): 2^x for two arguments without the MUFU.  x = n + f with n = round(x)
-// (magic-number rounding) and f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far
-// below the bf16 rounding of P), 2^n by adding n to the exponent field.  Arguments are clamped at -126 (masked scores
-// arrive as -inf and come out as 1e-38 instead of 0).
-__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, float& r1) {
-  const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
-  const f32x2 x = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-  const f32x2 t = add2(x, magic);                           // low mantissa bits = round(x) (two's complement)
-  const f32x2 f = fma2(add2(t, nmagic), pack2(-1.0f, -1.0f), x);  // x - round(x)
-  f32x2 q = fma2(pack2(5.517166480e-02f, 5.517166480e-02f), f, pack2(2.426111251e-01f, 2.426111251e-01f));
-  q = fma2(q, f, pack2(6.932609677e-01f, 6.932609677e-01f));
-  q = fma2(q, f, pack2(9.999280572e-01f, 9.999280572e-01f));
-  float q0, q1, t0, t1;
-  unpack2(q, q0, q1);
-  unpack2(t, t0, t1);
-  r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-  r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-}
-
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));

@@ -28,7 +28,8 @@ enum OpClass { CLS_CONV = 0, CLS_LINEAR = 1, CLS_ATTN = 2, CLS_GN = 3, CLS_LN = 
 struct Op {
   int cls;
   int launches;
-  double flops;
+  double flops;       // algorithmic (the reference op's FLOPs)
+  double exec_flops = -1;  // executed by the tensor core when that differs (folded upsample conv); -1: same as flops
   double bytes;
   std::function<cudaError_t(cudaStream_t)> run;
 };

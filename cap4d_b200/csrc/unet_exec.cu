@@ -542,11 +542,12 @@ struct Unet {
     }
   };
 
-  bool add_gemm_op(PlanCtx& c, int cls, const GemmPlan& plan) {
+  bool add_gemm_op(PlanCtx& c, int cls, const GemmPlan& plan, double exec_flops = -1) {
     Op op;
     op.cls = cls;
     op.launches = 1;
     op.flops = plan.flops;
+    op.exec_flops = exec_flops;
     op.bytes = 0;
     GemmPlan copy = plan;
     op.run = [copy](cudaStream_t s) { return launch_gemm(copy, s); };
@@ -739,8 +740,9 @@ struct Unet {
         if (!make_conv_plan(&p, pb, g, C, nullptr, 0, w.w + static_cast<size_t>(phase) * w.cout * 4 * C, w.cout, OUT_F32,
                             c.ptr<float>(*out), w.cout, w.b, nullptr, 1, 0, nullptr, 0))
           return false;
+        const double executed = p.flops;                            // 4 taps on the low-resolution grid
         p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C;  // algorithmic: the un-folded conv's share
-        add_gemm_op(c, CLS_CONV, p);
+        add_gemm_op(c, CLS_CONV, p, executed);
       }
     }
     c.release(xb);
@@ -1349,6 +1351,17 @@ int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int*
     if (bytes) bytes[op.cls] += op.bytes;
     if (launches) launches[op.cls] += op.launches;
   }
+  return 0;
+}
+
+int cap4d_b200_unet_class_exec_flops(void* handle, double* flops) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || flops == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  for (int k = 0; k < CAP4D_B200_N_CLASSES; ++k) flops[k] = 0;
+  for (const Op& op : u->ops) flops[op.cls] += (op.exec_flops >= 0 ? op.exec_flops : op.flops);
   return 0;
 }
 

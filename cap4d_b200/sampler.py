@@ -4,12 +4,16 @@
 reference `StochasticIOSampler.sample` (cap4d/mmdm/sampler.py:64-233): x_T from the global torch
 generator of the conditioning's device, per-step reference / generated-view permutations from the
 global numpy generator in the reference's order, float64->float32 DDIM factors.  What changes is
-where the data lives: conditioning and latents are uploaded once and stay in HBM, view groups are
-batched `groups_per_call` at a time into one U-Net launch plan, the CFG combine and the DDIM update
-are one fused kernel that scatters straight into the latent store, and with torch.distributed
-initialised (one rank per GPU, NCCL) the groups of a step are dealt round-robin to the ranks like
-the reference deals them to its device replicas (sampler.py:151-158), followed by one all-gather of
-the freshly updated latents per step.
+where the data lives.  Conditioning and latents are uploaded once and stay in HBM; the all-zero
+unconditional conditioning (cap4dcond.py:78-88) is neither stored nor uploaded; per step the host
+draws the permutations and sends the two index tables and the per-call parameters in ONE small
+copy; view groups are batched `groups_per_call` at a time, and one call = gather kernel (builds the
+U-Net batch from the stores through the index tables) -> U-Net -> fused CFG + DDIM update that
+scatters straight into the latent store.  That sequence is captured once per batch shape in a CUDA
+graph and replayed for every call of every step (everything that varies is read from device
+memory).  With torch.distributed initialised (one rank per GPU, NCCL) the groups of a step are
+dealt round-robin to the ranks like the reference deals them to its device replicas
+(sampler.py:151-158), followed by pack kernel -> one all-gather -> unpack kernel per step.
 """
 from __future__ import annotations
 
@@ -59,44 +63,200 @@ def _find_unet(model) -> B200MMDMUnet:
 
 
 class _SamplerState:
-    """Device-resident state of one sample() call."""
+    """State of one sample() call."""
+
+
+_KEYS = ("z_input", "ref_mask", "pos_enc")
 
 
 class _CudaBackend:
-    """The product data path: U-Net forward and fused CFG+DDIM update in libcap4d_b200.so."""
+    """The product data path: everything between the host's permutation draw and the updated latent store runs
+    in libcap4d_b200.so on device-resident data."""
 
-    def __init__(self, unet: B200MMDMUnet):
+    def __init__(self, unet: B200MMDMUnet, use_cuda_graph: bool = True):
         self.unet = unet
         self.device = unet.device
         self._lib = _lib.load()
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.graphs_captured = 0
+        self.graph_replays = 0
+        self.h2d_bytes = 0
 
-    def eps(self, x_in, t_in, control, n_ref_views=0):
-        # the groups are built as cat([ref, gen], dim=1): the first R views are reference views, and only the
-        # generated views' noise prediction is consumed (sampler.py:207-213)
-        return self.unet(x_in, timesteps=t_in, context=None, control=control, n_ref_views=n_ref_views)
+    # ---- one-time upload -----------------------------------------------------------------------
+    def _store(self, t: torch.Tensor, rows: int) -> torch.Tensor:
+        if t.device != self.device:
+            self.h2d_bytes += t.numel() * 4
+        return t.to(device=self.device, dtype=torch.float32, non_blocking=True).reshape(rows, -1).contiguous()
 
-    def cfg_ddim_update(self, latents, eps, gen_idx, n, V, R, chw, cfg_scale, x_f, e_f):
-        stream = torch.cuda.current_stream(self.device)
+    @staticmethod
+    def _all_zero(t: torch.Tensor) -> bool:
+        return not bool(torch.count_nonzero(t))
+
+    def begin(self, st, ref_cond, ref_uncond, gen_cond, gen_uncond, all_x) -> None:
+        dev = self.device
+        for d in (ref_cond, ref_uncond, gen_cond, gen_uncond):
+            if set(d.keys()) != set(_KEYS):
+                raise ValueError(f"conditioning dicts must hold exactly {_KEYS}")
+        zshape = gen_cond["z_input"].shape      # [n, 1, C, H, W]
+        pshape = gen_cond["pos_enc"].shape      # [n, 1, H, W, Cc]
+        st.C, st.H, st.W, st.Cc = int(zshape[-3]), int(zshape[-2]), int(zshape[-1]), int(pshape[-1])
+        if all_x.device != dev:
+            self.h2d_bytes += all_x.numel() * 4
+        st.latents = all_x.to(dev).reshape(st.n_gen, -1).contiguous()
+        keep = {}
+        stores = _lib.SamplerStores()
+        for prefix, cond, unc, rows in (("ref", ref_cond, ref_uncond, st.n_all_ref), ("gen", gen_cond, gen_uncond, st.n_gen)):
+            for key, field in (("z_input", "z"), ("ref_mask", "mask"), ("pos_enc", "pos")):
+                t = keep[f"{prefix}_{field}"] = self._store(cond[key], rows)
+                setattr(stores, f"{prefix}_{field}", t.data_ptr())
+                u = unc[key]
+                # the unconditional branch of CAP4DConditioning is zeros for z_input / pos_enc and the same
+                # ref_mask (cap4dcond.py:78-88): then there is nothing to keep or upload
+                redundant = torch.equal(u, cond[key]) if key == "ref_mask" else self._all_zero(u)
+                if redundant:
+                    setattr(stores, f"{prefix}_{field}_u", None)
+                else:
+                    tu = keep[f"{prefix}_{field}_u"] = self._store(u, rows)
+                    setattr(stores, f"{prefix}_{field}_u", tu.data_ptr())
+        stores.latents = st.latents.data_ptr()
+        st.stores, st.keep = stores, keep
+        # per-step host -> device block: [ref_idx int64 n_its*R | gen_idx int64 n_its*G | calls], double-buffered
+        n_calls = (len(range(st.rank, st.n_its, st.world)) + st.gpc - 1) // st.gpc
+        st.n_calls = n_calls
+        call_bytes = ctypes.sizeof(_lib.SamplerCall)
+        st.off_gen = st.n_its * st.R * 8
+        st.off_calls = st.off_gen + st.n_its * st.G * 8
+        st.block_bytes = st.off_calls + max(1, n_calls) * call_bytes
+        st.host_blocks = [torch.empty(st.block_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        st.host_events = [None, None]
+        st.dev_block = torch.empty(st.block_bytes, dtype=torch.uint8, device=dev)
+        st.dev_call = torch.empty(call_bytes, dtype=torch.uint8, device=dev)  # the slot the kernels read
+        st.call_bytes = call_bytes
+        st.bufs = {}    # n -> (x_in, z_in, mask, pos, t_in, eps)
+        st.graphs = {}  # n -> torch.cuda.CUDAGraph
+        st.xchg = None
+
+    # ---- per step ------------------------------------------------------------------------------
+    def start_step(self, st, ref_batches: np.ndarray, gen_batches: np.ndarray, step: int, x_f: float, e_f: float,
+                   my_groups: np.ndarray) -> None:
+        slot = st.i & 1
+        if st.host_events[slot] is not None:
+            st.host_events[slot].synchronize()  # the copy issued two steps ago has read this pinned block
+        hb = st.host_blocks[slot].numpy()
+        if st.R > 0:
+            hb[: st.off_gen].view(np.int64)[:] = ref_batches.reshape(-1)
+        hb[st.off_gen: st.off_calls].view(np.int64)[:] = gen_batches.reshape(-1)
+        calls = (_lib.SamplerCall * max(1, st.n_calls)).from_buffer(hb, st.off_calls)
+        for ci, c0 in enumerate(range(0, len(my_groups), st.gpc)):
+            grp = my_groups[c0:c0 + st.gpc]
+            calls[ci].timestep = int(step)
+            calls[ci].x_coef = x_f
+            calls[ci].e_coef = e_f
+            calls[ci].n_groups = len(grp)
+            for k, gidx in enumerate(grp):
+                calls[ci].groups[k] = int(gidx)
+        del calls
+        st.dev_block.copy_(st.host_blocks[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        st.host_events[slot] = ev
+        self.h2d_bytes += st.block_bytes
+
+    def _buffers(self, st, n: int):
+        b = st.bufs.get(n)
+        if b is None:
+            dev, V = self.device, st.V
+            f32 = dict(dtype=torch.float32, device=dev)
+            b = (torch.empty((2 * n, V, st.C, st.H, st.W), **f32), torch.empty((2 * n, V, st.C, st.H, st.W), **f32),
+                 torch.empty((2 * n, V, 1, st.H, st.W), **f32), torch.empty((2 * n, V, st.H, st.W, st.Cc), **f32),
+                 torch.empty((2 * n, V), dtype=torch.int64, device=dev),
+                 torch.empty((2 * n, V, st.C, st.H, st.W), **f32))
+            st.bufs[n] = b
+        return b
+
+    def _launch_call(self, st, n: int) -> None:
+        x_in, z_in, m_in, p_in, t_in, eps = self._buffers(st, n)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        ref_ptr = st.dev_block.data_ptr() if st.R > 0 else None
+        gen_ptr = st.dev_block.data_ptr() + st.off_gen
         _lib.check(
-            self._lib.cap4d_b200_cfg_ddim_update(latents.data_ptr(), eps.data_ptr(), gen_idx.data_ptr(), n, V, R, chw,
-                                                 float(cfg_scale), x_f, e_f, ctypes.c_void_p(stream.cuda_stream)),
-            "cfg_ddim_update",
-        )
+            self._lib.cap4d_b200_sampler_gather(ctypes.byref(st.stores), ref_ptr, gen_ptr, st.dev_call.data_ptr(), n,
+                                                st.V, st.R, st.C, st.H, st.W, st.Cc, x_in.data_ptr(), z_in.data_ptr(),
+                                                m_in.data_ptr(), p_in.data_ptr(), t_in.data_ptr(), stream),
+            "sampler_gather")
+        self.unet.forward_into(x_in, t_in, z_in, m_in, p_in, eps, n_ref_views=st.R)
+        _lib.check(
+            self._lib.cap4d_b200_sampler_update(st.latents.data_ptr(), eps.data_ptr(), gen_ptr, st.dev_call.data_ptr(), n,
+                                                st.V, st.R, st.chw, st.cfg_scale, stream),
+            "sampler_update")
+
+    def run_call(self, st, call_index: int, n: int) -> None:
+        """Groups `calls[call_index]` of the current step: gather -> U-Net -> CFG + DDIM scatter."""
+        with torch.cuda.device(self.device):
+            # the kernels (and the captured graph) read their parameters from one fixed device slot
+            off = st.off_calls + call_index * st.call_bytes
+            st.dev_call.copy_(st.dev_block[off: off + st.call_bytes], non_blocking=True)
+            # every record_every-th call is launched from the host with CUDA events around its kernels
+            # (B200MMDMUnet.record_every, bench.py's per-class times); a graph replay has no host side to time
+            rec = self.unet.record_every
+            if not self.use_cuda_graph or (rec and (self.unet._calls + 1) % rec == 0):
+                self._launch_call(st, n)
+                return
+            g = st.graphs.get(n)
+            if g is None:
+                self._launch_call(st, n)  # eager first: builds the launch plan, sets kernel attributes
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_call(st, n)
+                st.graphs[n] = g
+                self.graphs_captured += 1
+                # the eager run above already applied this call's update: restore nothing - the capture itself
+                # launches no work, so the step's arithmetic ran exactly once
+                return
+            g.replay()
+            self.unet._calls += 1
+            self.graph_replays += 1
+
+    # ---- multi-GPU -----------------------------------------------------------------------------
+    def exchange(self, st, dist) -> None:
+        """One all-gather per DDIM step: every rank contributes the views it just updated."""
+        per_rank = (st.n_its + st.world - 1) // st.world
+        if st.xchg is None:
+            st.xchg = (torch.zeros((per_rank * st.G, st.chw), device=self.device, dtype=torch.float32),
+                       torch.empty((st.world, per_rank * st.G, st.chw), device=self.device, dtype=torch.float32))
+        send, recv = st.xchg
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        gen_ptr = st.dev_block.data_ptr() + st.off_gen
+        _lib.check(self._lib.cap4d_b200_sampler_pack(st.latents.data_ptr(), gen_ptr, st.n_its, st.G, st.chw, st.rank,
+                                                     st.world, send.data_ptr(), stream), "sampler_pack")
+        dist.all_gather_into_tensor(recv.view(-1, st.chw), send)
+        _lib.check(self._lib.cap4d_b200_sampler_unpack(st.latents.data_ptr(), recv.data_ptr(), gen_ptr, st.n_its, st.G,
+                                                       st.chw, st.rank, st.world, stream), "sampler_unpack")
+
+    def end(self, st) -> torch.Tensor:
+        return st.latents.view(st.n_gen, *st.latent_shape)
 
 
 class B200StochasticIOSampler:
-    def __init__(self, model, groups_per_call: int = 1, backend=None, **kwargs):
-        """`backend` exists for the host-logic tests (gloo, CPU); the default and only shipped backend is
-        the CUDA library, which raises if the extension or a GPU is missing."""
+    def __init__(self, model, groups_per_call: int = 1, backend=None, use_cuda_graph: bool = True, **kwargs):
+        """`backend` exists for the host-logic tests (gloo, CPU): an object with `.device`, `eps(x_in, t_in,
+        control, n_ref_views)` and `cfg_ddim_update(...)` drives the same host logic through eager torch
+        indexing.  The default and only shipped backend is the CUDA library, which raises if the extension or a
+        GPU is missing."""
         if isinstance(model, dict):  # the reference's {device_key: model} map: this process drives ONE GPU
             model = next(iter(model.values()))
         self.main_model = model
-        self.backend = backend if backend is not None else _CudaBackend(_find_unet(model))
+        self.backend = backend if backend is not None else _CudaBackend(_find_unet(model), use_cuda_graph)
         self.ddpm_num_timesteps = model.num_timesteps
-        self.groups_per_call = max(1, int(groups_per_call))
-        self.h2d_bytes = 0
+        self.groups_per_call = max(1, min(int(groups_per_call), _lib.MAX_GROUPS_PER_CALL))
+        self._h2d_eager = 0
         self.d2h_bytes = 0
         self.unet_calls = 0
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self._h2d_eager + getattr(self.backend, "h2d_bytes", 0)
 
     # -- distributed helpers -------------------------------------------------------------------
     @staticmethod
@@ -111,7 +271,7 @@ class B200StochasticIOSampler:
         out = {}
         for k, v in d.items():
             if v.device != dev:
-                self.h2d_bytes += v.numel() * v.element_size()
+                self._h2d_eager += v.numel() * v.element_size()
             out[k] = v.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         return out
 
@@ -134,6 +294,7 @@ class B200StochasticIOSampler:
               eta=0.0) -> "_SamplerState":
         st = _SamplerState()
         dev = self.backend.device
+        _, st.rank, st.world = self._dist()
         st.mem_device = next(iter(gen_cond.values())).device
         st.n_gen = next(iter(gen_cond.values())).shape[0]
         st.n_all_ref = next(iter(ref_cond.values())).shape[0]
@@ -145,22 +306,27 @@ class B200StochasticIOSampler:
         st.steps, st.x_factors, st.e_factors = ddim_factors(self.main_model.alphas_cumprod, S, eta)
         st.n_steps = len(st.steps)
         st.cfg_scale = float(cfg_scale)
+        st.latent_shape = tuple(latent_shape)
+        st.chw = int(np.prod(latent_shape))
+        st.gpc = self.groups_per_call
+        st.i = 0
         # same generator, same call as the reference (sampler.py:112)
         all_x = torch.randn((st.n_gen, *latent_shape), device=st.mem_device)
-        if all_x.device != dev:
-            self.h2d_bytes += all_x.numel() * 4
-        st.latents = all_x.to(dev).contiguous()
-        st.rc, st.ru = self._upload(ref_cond, dev), self._upload(ref_uncond, dev)
-        st.gc, st.gu = self._upload(gen_cond, dev), self._upload(gen_uncond, dev)
-        st.chw = int(np.prod(latent_shape))
-        st.i = 0
+        st.device_plane = hasattr(self.backend, "run_call")
+        if st.device_plane:
+            self.backend.begin(st, ref_cond, ref_uncond, gen_cond, gen_uncond, all_x)
+        else:
+            if all_x.device != dev:
+                self._h2d_eager += all_x.numel() * 4
+            st.latents = all_x.to(dev).contiguous()
+            st.rc, st.ru = self._upload(ref_cond, dev), self._upload(ref_uncond, dev)
+            st.gc, st.gu = self._upload(gen_cond, dev), self._upload(gen_uncond, dev)
         return st
 
     @torch.no_grad()
     def step(self, st: "_SamplerState") -> None:
-        dev = self.backend.device
         dist, rank, world = self._dist()
-        n_its, R, V = st.n_its, st.R, st.V
+        n_its, R = st.n_its, st.R
         step = st.steps[st.i]
         # permutations: identical numpy consumption to sampler.py:131-139 (on every rank)
         if R == 1:
@@ -170,38 +336,50 @@ class B200StochasticIOSampler:
         gen_batches = np.reshape(np.random.permutation(np.arange(st.n_gen)), (n_its, -1))
         my_groups = np.arange(rank, n_its, world)  # round-robin like sampler.py:151-158
         x_f, e_f = float(st.x_factors[st.i]), float(st.e_factors[st.i])
-        rc, ru, gc, gu, latents = st.rc, st.ru, st.gc, st.gu, st.latents
-
-        for c0 in range(0, len(my_groups), self.groups_per_call):
-            grp = my_groups[c0:c0 + self.groups_per_call]
-            n = len(grp)
-            ref_idx = torch.from_numpy(ref_batches[grp]).to(dev, non_blocking=True)                       # [n, R]
-            gen_idx = torch.from_numpy(np.ascontiguousarray(gen_batches[grp])).to(dev, non_blocking=True)  # [n, G]
-            control = {}
-            for key in rc:
-                cond = torch.cat([rc[key][ref_idx], gc[key][gen_idx]], dim=1)
-                unc = torch.cat([ru[key][ref_idx], gu[key][gen_idx]], dim=1)
-                control[key] = torch.cat([unc, cond], dim=0)                                              # [2n, V, ...]
-            x_in = torch.cat([rc["z_input"][ref_idx], latents[gen_idx]], dim=1)
-            x_in = torch.cat([x_in, x_in], dim=0)
-            t_in = torch.full((2 * n, V), int(step), device=dev, dtype=torch.long)
-            eps = self.backend.eps(x_in, t_in, control, n_ref_views=R)
-            self.unet_calls += 1
-            self.backend.cfg_ddim_update(latents, eps, gen_idx, n, V, R, st.chw, st.cfg_scale, x_f, e_f)
-
-        if world > 1:
-            self._exchange(dist, rank, world, latents, gen_batches, n_its, st.G, st.chw)
+        if st.device_plane:
+            self.backend.start_step(st, ref_batches, gen_batches, int(step), x_f, e_f, my_groups)
+            for ci, c0 in enumerate(range(0, len(my_groups), st.gpc)):
+                self.backend.run_call(st, ci, len(my_groups[c0:c0 + st.gpc]))
+                self.unet_calls += 1
+            if world > 1:
+                self.backend.exchange(st, dist)
+        else:
+            self._step_eager(st, ref_batches, gen_batches, my_groups, int(step), x_f, e_f)
+            if world > 1:
+                self._exchange_eager(dist, rank, world, st.latents, gen_batches, n_its, st.G, st.chw)
         st.i += 1
 
     @torch.no_grad()
     def end(self, st: "_SamplerState") -> torch.Tensor:
-        out = st.latents.to(st.mem_device)
-        if out.device != st.latents.device:
+        lat = self.backend.end(st) if st.device_plane else st.latents
+        out = lat.to(st.mem_device)
+        if out.device != lat.device:
             self.d2h_bytes += out.numel() * 4
         return out
 
-    def _exchange(self, dist, rank, world, latents, gen_batches, n_its, G, chw):
-        """One all-gather per DDIM step: every rank contributes the views it just updated."""
+    # ---- host-logic test route (backend doubles): the same grouping through eager torch indexing -------------
+    def _step_eager(self, st, ref_batches, gen_batches, my_groups, step, x_f, e_f) -> None:
+        dev = self.backend.device
+        R, V = st.R, st.V
+        rc, ru, gc, gu, latents = st.rc, st.ru, st.gc, st.gu, st.latents
+        for c0 in range(0, len(my_groups), st.gpc):
+            grp = my_groups[c0:c0 + st.gpc]
+            n = len(grp)
+            ref_idx = torch.from_numpy(ref_batches[grp]).to(dev)                                    # [n, R]
+            gen_idx = torch.from_numpy(np.ascontiguousarray(gen_batches[grp])).to(dev)              # [n, G]
+            control = {}
+            for key in rc:
+                cond = torch.cat([rc[key][ref_idx], gc[key][gen_idx]], dim=1)
+                unc = torch.cat([ru[key][ref_idx], gu[key][gen_idx]], dim=1)
+                control[key] = torch.cat([unc, cond], dim=0)                                        # [2n, V, ...]
+            x_in = torch.cat([rc["z_input"][ref_idx], latents[gen_idx]], dim=1)
+            x_in = torch.cat([x_in, x_in], dim=0)
+            t_in = torch.full((2 * n, V), step, device=dev, dtype=torch.long)
+            eps = self.backend.eps(x_in, t_in, control, n_ref_views=R)
+            self.unet_calls += 1
+            self.backend.cfg_ddim_update(latents, eps, gen_idx, n, V, R, st.chw, st.cfg_scale, x_f, e_f)
+
+    def _exchange_eager(self, dist, rank, world, latents, gen_batches, n_its, G, chw):
         dev = latents.device
         per_rank = (n_its + world - 1) // world
         send = torch.zeros((per_rank * G, chw), device=dev, dtype=torch.float32)

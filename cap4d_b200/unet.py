@@ -311,6 +311,33 @@ class B200MMDMUnet(torch.nn.Module):
                 )
         return out.to(dtype=x.dtype) if x.dtype != torch.float32 else out
 
+    @torch.no_grad()
+    def forward_into(self, x, timesteps, z_input, ref_mask, pos_enc, out, n_ref_views: int = 0) -> None:
+        """The same forward on caller-owned, contiguous fp32 device tensors (x, z_input, out [B, V, C, H, W];
+        ref_mask [B, V, 1, H, W]; pos_enc [B, V, H, W, Cc]; timesteps int64 [B, V]): nothing is allocated or
+        copied, so the call can be captured in a CUDA graph (B200StochasticIOSampler does)."""
+        B, V, C, H, W = x.shape
+        with torch.cuda.device(self._device):
+            ws = self._workspace(B, V, H, W, int(n_ref_views))
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            self._calls += 1
+            if self.record_every and self._calls % self.record_every == 0 and not torch.cuda.is_current_stream_capturing():
+                _lib.check(
+                    self._lib.cap4d_b200_unet_forward_timed(self._handle, x.data_ptr(), timesteps.data_ptr(),
+                                                            z_input.data_ptr(), ref_mask.data_ptr(), pos_enc.data_ptr(),
+                                                            out.data_ptr(), B, V, H, W, ws.data_ptr(), ws.numel(),
+                                                            ctypes.c_void_p(stream), None),
+                    "unet_forward_timed",
+                )
+            else:
+                _lib.check(
+                    self._lib.cap4d_b200_unet_forward(self._handle, x.data_ptr(), timesteps.data_ptr(),
+                                                      z_input.data_ptr(), ref_mask.data_ptr(), pos_enc.data_ptr(),
+                                                      out.data_ptr(), B, V, H, W, ws.data_ptr(), ws.numel(),
+                                                      ctypes.c_void_p(stream)),
+                    "unet_forward",
+                )
+
     def collect_timings(self):
         """Per-class ms summed over the recorded forwards since the last call -> ({class: ms}, n_forwards)."""
         self._ensure_built()
@@ -344,7 +371,10 @@ class B200MMDMUnet(torch.nn.Module):
         by = (ctypes.c_double * _lib.N_CLASSES)()
         ln = (ctypes.c_int * _lib.N_CLASSES)()
         _lib.check(self._lib.cap4d_b200_unet_class_stats(self._handle, fl, by, ln), "class_stats")
-        return {n: dict(flops=fl[i], bytes=by[i], launches=ln[i]) for i, n in enumerate(_lib.CLASS_NAMES)}
+        ex = (ctypes.c_double * _lib.N_CLASSES)()
+        _lib.check(self._lib.cap4d_b200_unet_class_exec_flops(self._handle, ex), "class_exec_flops")
+        return {n: dict(flops=fl[i], exec_flops=ex[i], bytes=by[i], launches=ln[i])
+                for i, n in enumerate(_lib.CLASS_NAMES)}
 
     def num_launches(self) -> int:
         self._ensure_built()

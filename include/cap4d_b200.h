@@ -97,6 +97,10 @@ int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timeste
 #define CAP4D_B200_N_CLASSES 6
 int cap4d_b200_unet_num_launches(void* handle, int* n);
 int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int* launches);
+/* class_stats reports ALGORITHMIC FLOPs (the reference op's count); this returns what the tensor core executes per
+ * class, which is less where an op was restructured (nearest-2x upsample + conv3x3 folded into four 2x2-tap phase
+ * convolutions: 4/9 of the multiply-adds). */
+int cap4d_b200_unet_class_exec_flops(void* handle, double* flops);
 int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* timesteps, const float* z_input,
                                   const float* ref_mask, const float* pos_enc, float* out, int B, int V, int H,
                                   int W, void* workspace, size_t workspace_bytes, void* stream, float* class_ms);
@@ -111,6 +115,59 @@ int cap4d_b200_unet_destroy(void* handle);
  *   e = eps_u + cfg * (eps_c - eps_u);  latents[gen_idx[g][v-R]] = latents[..] * x_coef + e * e_coef */
 int cap4d_b200_cfg_ddim_update(float* latents, const float* eps, const int64_t* gen_idx, int n_groups, int V, int R,
                                int chw, float cfg_scale, float x_coef, float e_coef, void* stream);
+
+/* ---- device-resident sampler data plane: replaces cap4d/mmdm/sampler.py:141-213 ----------------
+ * The reference keeps every tensor on the CPU and, per view group, indexes the conditioning dicts, concatenates
+ * reference and generated views (dim 1) and the unconditional and conditional halves (dim 0), and copies the
+ * result to the GPU.  Here the stores are uploaded once per sample() call and stay in HBM. */
+#define CAP4D_B200_MAX_GROUPS_PER_CALL 16
+
+/* Rows are views: *_z [n][C*H*W] (control["z_input"]), *_mask [n][H*W] (control["ref_mask"]), *_pos [n][H*W*Cc]
+ * (control["pos_enc"]); ref_* index the reference views, gen_* the generated views; latents [n_gen][C*H*W] is
+ * all_x_T (sampler.py:112).  The *_u members are the unconditional dicts (ref_uncond / gen_uncond): NULL means what
+ * CAP4DConditioning produces for unconditional=True (cap4dcond.py:78-88): zeros for z_input and pos_enc, the
+ * conditional ref_mask - in which case nothing is stored, uploaded or read for them. */
+typedef struct cap4d_b200_sampler_stores {
+  const float *ref_z, *ref_mask, *ref_pos;
+  const float *gen_z, *gen_mask, *gen_pos;
+  const float *ref_z_u, *ref_mask_u, *ref_pos_u;
+  const float *gen_z_u, *gen_mask_u, *gen_pos_u;
+  float* latents;
+} cap4d_b200_sampler_stores;
+
+/* What changes from call to call, read by the kernels from DEVICE memory (a captured CUDA graph is replayed with
+ * new contents): the DDIM timestep of the step (sampler.py:124), its x / e_t factors (sampler.py:215-229) and the
+ * view groups (rows of the step's index tables) this call processes. */
+typedef struct cap4d_b200_sampler_call {
+  int64_t timestep;
+  float x_coef, e_coef;
+  int32_t n_groups, pad_;
+  int32_t groups[CAP4D_B200_MAX_GROUPS_PER_CALL];
+} cap4d_b200_sampler_call;
+
+/* sampler.py:161-195 for n_groups groups at once: builds x_in / control / t_in of the batch
+ * [uncond group 0..n-1 | cond group 0..n-1] x V views (first R views = reference views) in the caller's buffers
+ * x_in, z_in [2n][V][C][H][W], mask_in [2n][V][1][H][W], pos_in [2n][V][H][W][Cc], t_in int64 [2n][V].
+ * ref_idx int64 [n_its][R] and gen_idx int64 [n_its][G] are the step's ref_batches / gen_batches
+ * (sampler.py:131-139) in device memory; `call` is a DEVICE pointer. */
+int cap4d_b200_sampler_gather(const cap4d_b200_sampler_stores* stores, const int64_t* ref_idx, const int64_t* gen_idx,
+                              const cap4d_b200_sampler_call* call, int n_groups, int V, int R, int C, int H, int W,
+                              int Cc, float* x_in, float* z_in, float* mask_in, float* pos_in, int64_t* t_in,
+                              void* stream);
+
+/* cap4d_b200_cfg_ddim_update with the groups, gen_idx rows and DDIM factors taken from `call` (device memory). */
+int cap4d_b200_sampler_update(float* latents, const float* eps, const int64_t* gen_idx,
+                              const cap4d_b200_sampler_call* call, int n_groups, int V, int R, int chw, float cfg_scale,
+                              void* stream);
+
+/* Per-step latent exchange between ranks (one process per GPU; rank r owns groups r, r + world, ... like the
+ * reference deals groups to its device replicas, sampler.py:151-158): pack the views this rank updated into
+ * send [ceil(n_its / world) * G][chw], all-gather (caller, NCCL), then unpack every other rank's block of
+ * recv [world][ceil(n_its / world) * G][chw] into the latent store. */
+int cap4d_b200_sampler_pack(const float* latents, const int64_t* gen_idx, int n_its, int G, int chw, int rank,
+                            int world, float* send, void* stream);
+int cap4d_b200_sampler_unpack(float* latents, const float* recv, const int64_t* gen_idx, int n_its, int G, int chw,
+                              int rank, int world, void* stream);
 
 /* ---- single-kernel entry points (building blocks; used by tests and micro-benchmarks) --------
  * bf16 tensors are passed as uint16_t*. */

@@ -286,6 +286,12 @@ def res_block(sd, p, x, emb):
     return x + h
 
 
+# "legacy": the reference's materialised softmax (what the parity tests check against).  "sdpa": the same contraction
+# through torch's fused scaled_dot_product_attention - only for bench.py's gpu_eager_baseline leg (the best stock
+# PyTorch can do on the same GPU); never used as a checker.
+ATTENTION_IMPL = "legacy"
+
+
 def attention_core(q, k, v, heads: int, views: int, is3d: bool):
     """AttentionModule.forward 'NORMAL ATTENTION' branch + legacy_attention
     (cap4d/mmdm/net/attention.py:229-251, :112-132): softmax(q k^T / sqrt(d)) v, fp32."""
@@ -303,9 +309,12 @@ def attention_core(q, k, v, heads: int, views: int, is3d: bool):
             return y.reshape(bt, n, heads, d).permute(0, 2, 1, 3).reshape(bt * heads, n, d)
 
     q, k, v = split(q), split(k), split(v)
-    sim = torch.einsum("bid,bjd->bij", q.float(), k.float()) * (d ** -0.5)
-    sim = sim.softmax(dim=-1)
-    out = torch.einsum("bij,bjd->bid", sim, v)
+    if ATTENTION_IMPL == "sdpa":
+        out = F.scaled_dot_product_attention(q[None], k[None], v[None], scale=d ** -0.5)[0]
+    else:
+        sim = torch.einsum("bid,bjd->bij", q.float(), k.float()) * (d ** -0.5)
+        sim = sim.softmax(dim=-1)
+        out = torch.einsum("bij,bjd->bid", sim, v)
     if is3d:
         out = out.reshape(b, heads, n, views, d).permute(0, 3, 2, 1, 4).reshape(bt, n, c)
     else:
