@@ -19,6 +19,7 @@ download of the latents inside the timed region).  With N > 1 the SAME 840-view 
 the ranks (strong scaling; groups dealt round-robin, one NCCL all-gather of updated latents/step).
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -157,7 +158,8 @@ def _cpu_forward_fn(R):
 
         if not RI.reference_available():
             raise RuntimeError("no reference copy")
-        ref = RI.build_reference_unet(cfg)
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints while importing / constructing
+            ref = RI.build_reference_unet(cfg)
         ref.load_state_dict(sd)
         del sd
 
@@ -262,7 +264,8 @@ def gpu_eager_baseline(dev, G, R):
             from oracle import ref_import as RI
 
             if RI.reference_available():
-                ref = RI.build_reference_unet(cfg)
+                with contextlib.redirect_stdout(sys.stderr):
+                    ref = RI.build_reference_unet(cfg)
                 ref.load_state_dict({k: v.cpu() for k, v in sd.items()})
                 ref = ref.to(dev)
         except Exception as e:
@@ -387,8 +390,10 @@ def main():
     calls0 = sampler.unet_calls
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    torch.cuda.nvtx.range_push("bench_timed")  # ncu --nvtx --nvtx-include "bench_timed/" profiles this region only
     for _ in range(K):
         sampler.step(st)
+    torch.cuda.nvtx.range_pop()
     ev1.record()
     barrier()
     unet.record_every = 0

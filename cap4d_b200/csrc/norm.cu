@@ -75,7 +75,7 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img, int resident) {
   const int fill = (waves * resident + n_img - 1) / n_img;                   // (2) enough items
   if (chunks < fill) chunks = fill;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks > resident) chunks = resident;  // an image's chunks must fit two pipeline stages (see the kernel)
+  if (chunks > resident) chunks = resident;  // never more chunks per image than blocks (see the kernel's ticket loop)
   int rpc = (hw + chunks - 1) / chunks;
   if (rpc < 4 * g.TY) rpc = 4 * g.TY;
   if (rpc > hw) rpc = hw;
@@ -93,7 +93,8 @@ __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const fl
 }
 
 // ---- GroupNorm (+SiLU), one persistent cooperative kernel ----------------------------------------
-// Work item = (image n, chunk of rows), items in image-major order, block b takes items b, b + grid, ...
+// Work item = (image n, chunk of rows), items in image-major order, drawn by the resident blocks from a ticket
+// counter.
 // Block (TX, TY): thread (tx, ty) owns channel quads tx + i*TX (i < NQI) and rows ty, ty+TY, ... of the chunk,
 // UNROLL rows (= UNROLL*NQI independent 16 B loads) per iteration.
 //   phase 1  per-chunk (sum, sumsq) of the 32 groups -> partial[n][chunk][g][2], then arrive on the image's
@@ -106,18 +107,20 @@ __device__ __forceinline__ float4 ld_quad(const float* __restrict__ x1, const fl
 // item k, so the barrier latency hides behind useful loads and a block never idles at a barrier while it
 // still has statistics to contribute.  Waiting on other blocks is legitimate here because the launch is
 // cooperative (cudaLaunchCooperativeKernel: the runtime refuses the launch unless every block is resident)
-// and an image's chunks sit in at most two consecutive pipeline stages (n_chunks <= grid): the wait of
-// stage k only needs phase 1 of stages k and k+1, which no block defers behind a later wait.
+// and an image never has more chunks than there are blocks (see the ticket loop at the end of the kernel).
 // All counters return to zero by the end of the launch (graph replays need no reset).
 struct GnSync {
   unsigned int arrived, ready, done;
+};
+struct GnTicket {
+  unsigned int next, left;
 };
 
 template <int NQI, int UNROLL>
 __global__ void __launch_bounds__(GN_THREADS, (NQI == 1) ? 4 : 2)
 gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2, int hw, int cpg,
                 int rows_per_chunk, int n_chunks, int n_img, float* __restrict__ partial, float2* __restrict__ stats,
-                GnSync* __restrict__ sync, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                GnSync* __restrict__ sync, GnTicket* __restrict__ ticket, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 int apply_silu, bf16* __restrict__ out, bf16* __restrict__ raw_out, int x2_G, int x2_V, int x2_R,
                 int pipelined) {
   extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
@@ -323,9 +326,21 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     }
   };
 
+  // Items are handed out in order by a global ticket counter (dynamic balance: a block that drew slow chunks does
+  // not hold a fixed share back).  Deadlock freedom with tickets: the drawn items always form a prefix of the item
+  // order; a block only waits while holding two drawn items, so if every block waited on the same unfinished image
+  // that image would have 2 x grid > n_chunks drawn chunks - impossible with n_chunks <= grid.
+  __shared__ int s_item;
+  auto draw = [&]() {
+    __syncthreads();  // everybody is done with the previous value of s_item
+    if (tid == 0) s_item = static_cast<int>(atomicAdd(&ticket->next, 1u));
+    __syncthreads();
+    return s_item;
+  };
   if (pipelined) {
     int prev = -1;
-    for (int item = blockIdx.x;; item += gridDim.x) {
+    for (;;) {
+      const int item = draw();
       const bool has = item < n_items;
       if (has) phase1(item);
       if (prev >= 0) phase2(prev);
@@ -333,9 +348,19 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
       prev = item;
     }
   } else {
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = draw(); item < n_items; item = draw()) {
       phase1(item);
       phase2(item);
+    }
+  }
+  // the last block to leave rewinds the ticket counter for the next launch
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int left = atomicAdd(&ticket->left, 1u);
+    if (left == gridDim.x - 1u) {
+      ticket->next = 0u;
+      ticket->left = 0u;
+      __threadfence();
     }
   }
 }
@@ -423,7 +448,7 @@ cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_
   }
   g = gn_geometry(C1, C2, hw, n_img, resident);
   const int n_items = n_img * g.n_chunks;
-  // n_chunks <= grid keeps an image's chunks within two pipeline stages (see the kernel's header)
+  // n_chunks <= grid is what makes the ticket loop deadlock-free (see the kernel)
   int grid = resident;
   if (grid > n_items) grid = n_items;
   if (grid < g.n_chunks) {
@@ -434,9 +459,10 @@ cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_
   // scratch: partials | per-image group statistics | per-image counters (zero between launches)
   float2* stats = reinterpret_cast<float2*>(partial + static_cast<size_t>(n_layout) * GN_MAX_CHUNKS * GN_GROUPS * 2);
   GnSync* sync = reinterpret_cast<GnSync*>(stats + static_cast<size_t>(n_layout) * GN_GROUPS);
+  GnTicket* ticket = reinterpret_cast<GnTicket*>(sync + n_layout);
   int cpg = g.cpg, rpc = g.rows_per_chunk, nch = g.n_chunks;
   static int pipelined = env_int("CAP4D_GN_PIPELINE", 1);
-  void* args[] = {&x1, &x2, &C1, &C2, &hw, &cpg, &rpc, &nch, &n_img, &partial, &stats, &sync, &gamma, &beta, &eps,
+  void* args[] = {&x1, &x2, &C1, &C2, &hw, &cpg, &rpc, &nch, &n_img, &partial, &stats, &sync, &ticket, &gamma, &beta, &eps,
                   &apply_silu, &out, &raw_out, &x2_G, &x2_V, &x2_R, &pipelined};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_fused_kernel<NQI, UNROLL>), dim3(grid), block,
                                      args, smem, stream);
@@ -450,7 +476,9 @@ size_t groupnorm_sync_offset(int n_img) {
   return static_cast<size_t>(n_img) * GN_MAX_CHUNKS * GN_GROUPS * 2 * sizeof(float) +
          static_cast<size_t>(n_img) * GN_GROUPS * sizeof(float2);
 }
-size_t groupnorm_partial_bytes(int n_img) { return groupnorm_sync_offset(n_img) + static_cast<size_t>(n_img) * sizeof(GnSync); }
+size_t groupnorm_partial_bytes(int n_img) {
+  return groupnorm_sync_offset(n_img) + static_cast<size_t>(n_img) * sizeof(GnSync) + sizeof(GnTicket);
+}
 
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
