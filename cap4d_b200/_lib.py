@@ -95,6 +95,10 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
          c_size_t, c_void_p, POINTER(c_float)],
     ),
+    "cap4d_b200_unet_enable_taps": (c_int, [c_void_p, c_int]),
+    "cap4d_b200_unet_num_taps": (c_int, [c_void_p, POINTER(c_int)]),
+    "cap4d_b200_unet_tap_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_void_p), POINTER(c_int64),
+                                         POINTER(c_int), POINTER(c_int)]),
     "cap4d_b200_unet_collect_timings": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
     "cap4d_b200_unet_destroy": (c_int, [c_void_p]),
     "cap4d_b200_cfg_ddim_update": (
@@ -108,6 +112,9 @@ SIGNATURES = {
     "cap4d_b200_sampler_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cap4d_b200_gemm_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                POINTER(c_float), c_int]),
+    "cap4d_b200_gemm_mixed": (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                 POINTER(c_float), c_int]),
     "cap4d_b200_conv3x3_bf16": (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,6 +1,8 @@
 // Data-movement and small fp32 kernels around the tensor-core path: input pack (ref-mask mix +
 // im2col of the 4-channel latent + pose conditioning), output mix, up/down-sampling layout
 // transforms, the timestep-embedding MLPs, weight repacking and the fused CFG + DDIM update.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -14,7 +16,7 @@ namespace {
 //                  else 0
 __global__ void input_pack_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                   const float* __restrict__ mask, const float* __restrict__ pos, int n_img, int cin,
-                                  int H, int W, int cc, int kpad, bf16* __restrict__ out) {
+                                  int H, int W, int cc, int kpad, bf16* __restrict__ out, int out_f16) {
   const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -37,7 +39,12 @@ __global__ void input_pack_kernel(const float* __restrict__ x, const float* __re
     } else if (k < 9 * cin + cc) {
       v = pos[pix * cc + (k - 9 * cin)];
     }
-    out[i] = __float2bfloat16(v);
+    if (out_f16) {
+      const __half hv = __float2half_rn(v);
+      out[i] = *reinterpret_cast<const bf16*>(&hv);
+    } else {
+      out[i] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -307,8 +314,17 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ src, int ld, int 
 }
 
 // ---- weight repacks ---------------------------------------------------------------------------
+// 16-bit storage of a weight: bf16, or the fp16 bit pattern in the same 2 bytes (kernels.h: set_weight_pack_f16)
+__device__ __forceinline__ bf16 w16(float v, int f16) {
+  if (f16) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const bf16*>(&h);
+  }
+  return __float2bfloat16(v);
+}
+
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW,
-                                        bf16* __restrict__ out, int ldk, int k_offset) {
+                                        bf16* __restrict__ out, int ldk, int k_offset, int f16) {
   const size_t total = static_cast<size_t>(O) * I * KH * KW;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -317,23 +333,23 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
     const int tap = static_cast<int>((idx / I) % (KH * KW));
     const size_t o = idx / (static_cast<size_t>(I) * KH * KW);
     const float v = w[(o * I + i) * KH * KW + tap];
-    out[o * ldk + k_offset + static_cast<size_t>(tap) * I + i] = __float2bfloat16(v);
+    out[o * ldk + k_offset + static_cast<size_t>(tap) * I + i] = w16(v, f16);
   }
 }
 
 __global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int cols, bf16* __restrict__ out, int ldk,
-                                   int k_offset, int row_offset) {
+                                   int k_offset, int row_offset, int f16) {
   const size_t total = static_cast<size_t>(rows) * cols;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t r = idx / cols, c = idx % cols;
-    out[(row_offset + r) * ldk + k_offset + c] = __float2bfloat16(w[idx]);
+    out[(row_offset + r) * ldk + k_offset + c] = w16(w[idx], f16);
   }
 }
 
 // ---- folded upsample-conv weights (openaimodel.py:111-119) ---------------------------------------
 // phase py: output row 2y+py reads low-res rows {y-1 (ky=0), y (ky=1,2)} if py == 0, {y (ky=0,1), y+1 (ky=2)} if py == 1
-__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int O, int I, bf16* __restrict__ out) {
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int O, int I, bf16* __restrict__ out, int f16) {
   const size_t total = static_cast<size_t>(4) * O * 4 * I;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -350,7 +366,7 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int O, in
     float acc = 0.f;
     for (int ky = ky0; ky <= ky1; ++ky)
       for (int kx = kx0; kx <= kx1; ++kx) acc += w[((o * I + i) * 3 + ky) * 3 + kx];
-    out[idx] = __float2bfloat16(acc);
+    out[idx] = w16(acc, f16);
   }
 }
 
@@ -409,10 +425,10 @@ inline int grid_for(size_t total, int block) {
 
 cudaError_t launch_input_pack(const float* x, const float* z_input, const float* ref_mask, const float* pos_enc,
                               int n_img, int cin, int H, int W, int ccond, int kpad, bf16* out,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int out_f16) {
   const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
   input_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, z_input, ref_mask, pos_enc, n_img, cin, H, W, ccond,
-                                                              kpad, out);
+                                                              kpad, out, out_f16);
   return cudaGetLastError();
 }
 
@@ -472,16 +488,20 @@ cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int e
   return cudaGetLastError();
 }
 
+static thread_local bool g_pack_f16 = false;
+void set_weight_pack_f16(bool f16) { g_pack_f16 = f16; }
+bool weight_pack_f16() { return g_pack_f16; }
+
 cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
                                     int k_offset, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(O) * I * KH * KW;
-  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset);
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset, weight_pack_f16() ? 1 : 0);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(16) * O * I;
-  pack_upconv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, out);
+  pack_upconv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, out, weight_pack_f16() ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -497,7 +517,8 @@ cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t s
 cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, int ldk, int k_offset, int row_offset,
                                cudaStream_t stream) {
   const size_t total = static_cast<size_t>(rows) * cols;
-  pack_matrix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, rows, cols, out, ldk, k_offset, row_offset);
+  pack_matrix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, rows, cols, out, ldk, k_offset, row_offset,
+                                                               weight_pack_f16() ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -216,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, p.BN, 0);
+      const uint32_t idesc = umma_idesc_bf16(BM, p.BN, 0, p.a_f16, p.b_f16);
       const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(sA));  // stage / sub-tile / k offsets are added
       const uint64_t bdesc0 = umma_smem_desc_sw128(smem_u32(sB));  // to the 14-bit (>>4) address field
       int stage = 0;
@@ -500,7 +500,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader_cta) {
-      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN, 0);
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN, 0, p.a_f16, p.b_f16);
       const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(sA));
       const uint64_t bdesc0 = umma_smem_desc_sw128(smem_u32(sB));
       int stage = 0;

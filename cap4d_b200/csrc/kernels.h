@@ -53,6 +53,7 @@ struct GemmParams {
   int rowbias_div, rowbias_ld;
   const float* residual;  // fp32 [M][ldr] or null
   int ldr;
+  int a_f16, b_f16;  // operand storage formats: 0 = bf16, 1 = fp16 (set after make_*_plan; default bf16 x bf16)
 };
 
 struct GemmPlan {
@@ -127,13 +128,14 @@ enum { GN_MAX_CHUNKS = 128 };
 // zeroed for when that is more than n_img (0 = n_img).
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
-                             cudaStream_t stream, int x2_G = 0, int x2_V = 0, int x2_R = 0, int n_img_layout = 0);
+                             cudaStream_t stream, int x2_G = 0, int x2_V = 0, int x2_R = 0, int n_img_layout = 0,
+                             int out_f16 = 0);  // out_f16: `out` is written as fp16 (raw_out stays bf16)
 size_t groupnorm_partial_bytes(int n_img);
 size_t groupnorm_sync_offset(int n_img);  // the bytes from here to the end must be zero before the first launch
 
 // LayerNorm over the last dim of fp32 [M][C] -> bf16 [M][C]
 cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
-                             bf16* out, cudaStream_t stream);
+                             bf16* out, cudaStream_t stream, int out_f16 = 0);
 
 // ---------------------------------------------------------------------------
 // Elementwise / data-movement (elementwise.cu)
@@ -143,7 +145,7 @@ cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, c
 // columns: [9*cin im2col | ccond pos_enc | 0...].
 cudaError_t launch_input_pack(const float* x, const float* z_input, const float* ref_mask, const float* pos_enc,
                               int n_img, int cin, int H, int W, int ccond, int kpad, bf16* out,
-                              cudaStream_t stream);
+                              cudaStream_t stream, int out_f16 = 0);
 // Output stage (mmdm_unet.py:118-125): eps = x_input*mask + h*(1-mask), NHWC(ld) -> [n_img][cout][H][W]
 cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const float* z_input, const float* ref_mask,
                               int n_img, int cout, int H, int W, int G, int V, int R, float* out,
@@ -167,7 +169,11 @@ size_t time_embed_scratch_bytes(int n_img, int model_ch, int emb_ch);
 // eps: [2*n_groups][V][chw] (uncond halves first, then cond halves), R leading reference views skipped.
 cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long long* gen_idx, int n_groups, int V,
                                    int R, int chw, float cfg, float x_coef, float e_coef, cudaStream_t stream);
-// fp32 -> bf16 weight repacks (device side)
+// fp32 -> 16-bit weight repacks (device side).  The target format is bf16 unless set_weight_pack_f16(true) is in
+// effect (thread-local; the executor sets it around its finalize): then the same buffers receive fp16 bit patterns
+// and the GEMM plans that read them carry b_f16 = 1.
+void set_weight_pack_f16(bool f16);
+bool weight_pack_f16();
 cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
                                     int k_offset, cudaStream_t stream);  // out[o][k_offset + (kh*KW+kw)*I + i]
 // nearest-2x-upsample + conv3x3 folded: out[phase][o][(a*2+b)*I + i] = sum of the 3x3 taps that fall on

@@ -122,7 +122,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
                 int rows_per_chunk, int n_chunks, int n_img, float* __restrict__ partial, float2* __restrict__ stats,
                 GnSync* __restrict__ sync, GnTicket* __restrict__ ticket, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 int apply_silu, bf16* __restrict__ out, bf16* __restrict__ raw_out, int x2_G, int x2_V, int x2_R,
-                int pipelined) {
+                int pipelined, int out_f16) {
   extern __shared__ float s_ch[];  // [TY][2][C]: per-row-lane channel partials (no atomics: deterministic)
   __shared__ double s_part[8][GN_GROUPS][2];
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -292,7 +292,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
         y2 = silu_f(y2);
         y3 = silu_f(y3);
       }
-      __stcs(reinterpret_cast<uint2*>(out + row * C + c), make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3)));
+      __stcs(reinterpret_cast<uint2*>(out + row * C + c), make_uint2(pack16x2(y0, y1, out_f16), pack16x2(y2, y3, out_f16)));
       if (raw_out != nullptr)
         __stcs(reinterpret_cast<uint2*>(raw_out + row * C + c), make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)));
     };
@@ -369,7 +369,7 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 template <int NQ>  // quads per lane: C <= 128 * NQ
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
+                 const float* __restrict__ beta, float eps, bf16* __restrict__ out, int out_f16) {
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -414,7 +414,7 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
       const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
       const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
       const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
-      *reinterpret_cast<uint2*>(orow + qd * 4) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      *reinterpret_cast<uint2*>(orow + qd * 4) = make_uint2(pack16x2(y0, y1, out_f16), pack16x2(y2, y3, out_f16));
     }
   }
 }
@@ -435,7 +435,7 @@ int gn_resident_blocks(size_t smem_bytes, int threads) {
 template <int NQI>
 cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_img, int hw, const float* gamma,
                         const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
-                        cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_layout) {
+                        cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_layout, int out_f16) {
   constexpr int UNROLL = (NQI >= 4) ? 2 : 4;
   const int C = C1 + C2;
   // the block shape does not depend on the residency, the residency depends on the block's shared memory
@@ -463,7 +463,7 @@ cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_
   int cpg = g.cpg, rpc = g.rows_per_chunk, nch = g.n_chunks;
   static int pipelined = env_int("CAP4D_GN_PIPELINE", 1);
   void* args[] = {&x1, &x2, &C1, &C2, &hw, &cpg, &rpc, &nch, &n_img, &partial, &stats, &sync, &ticket, &gamma, &beta, &eps,
-                  &apply_silu, &out, &raw_out, &x2_G, &x2_V, &x2_R, &pipelined};
+                  &apply_silu, &out, &raw_out, &x2_G, &x2_V, &x2_R, &pipelined, &out_f16};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_fused_kernel<NQI, UNROLL>), dim3(grid), block,
                                      args, smem, stream);
 }
@@ -482,7 +482,7 @@ size_t groupnorm_partial_bytes(int n_img) {
 
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
-                             cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_img_layout) {
+                             cudaStream_t stream, int x2_G, int x2_V, int x2_R, int n_img_layout, int out_f16) {
   const int C = C1 + C2;
   const int n_layout = n_img_layout > 0 ? n_img_layout : n_img;
   if (C % GN_GROUPS != 0 || C1 % 4 != 0 || C2 % 4 != 0) {
@@ -497,7 +497,7 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
   }
 #define CAP4D_GN_CASE(N) \
   return launch_gn_t<N>(C1, C2, x1, x2, n_img, hw, gamma, beta, eps, apply_silu, out, raw_out, partial, stream, x2_G, \
-                        x2_V, x2_R, n_layout)
+                        x2_V, x2_R, n_layout, out_f16)
   if (g.nqi == 1) CAP4D_GN_CASE(1);
   if (g.nqi == 2) CAP4D_GN_CASE(2);
   CAP4D_GN_CASE(4);
@@ -505,7 +505,7 @@ cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, i
 }
 
 cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
-                             bf16* out, cudaStream_t stream) {
+                             bf16* out, cudaStream_t stream, int out_f16) {
   if (C % 4 != 0 || C > 4 * 32 * 16) {
     set_error("layernorm: C must be a multiple of 4 and <= 2048");
     return cudaErrorInvalidValue;
@@ -514,11 +514,11 @@ cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, c
   const int grid = (M + warps - 1) / warps;
   const int quads = C / 4;
   if (quads <= 32 * 4)
-    layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+    layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
   else if (quads <= 32 * 8)
-    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
   else
-    layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out);
+    layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
   return cudaGetLastError();
 }
 

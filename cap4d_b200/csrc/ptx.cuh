@@ -265,12 +265,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M = 128.
-//   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
+// Instruction descriptor for kind::f16, {bf16 | fp16} x {bf16 | fp16} -> fp32, M = 128.
+//   [4,6) D fmt (1 = f32)  [7,10) A fmt (0 = fp16, 1 = bf16)  [10,13) B fmt (0 = fp16, 1 = bf16)
 //   [15] A major (0 = K)   [16] B major (0 = K, 1 = MN)
 //   [17,23) N >> 3         [24,29) M >> 4
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// The two operand formats are independent fields: activations stay bf16 (range) while weights, whose range is
+// known, are stored as fp16 (three more mantissa bits: weight rounding is half of the bf16 path's error budget).
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major,
+                                                             uint32_t a_f16 = 0, uint32_t b_f16 = 0) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
@@ -353,6 +357,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// two floats -> one 32-bit word of bf16x2 (f16 == 0) or fp16x2 (f16 != 0): the 16-bit storage format of an MMA
+// operand is a property of the tensor (fp16 where the producing norm bounds the range, bf16 elsewhere)
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
+  if (f16) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  return pack_bf16x2(lo, hi);
 }
 
 // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU (tanh.approx, |err| ~ 2^-11) instead of ex2 + rcp; the

@@ -7,11 +7,14 @@
 // every intermediate carved out of a caller-provided workspace (no allocation after planning).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <string>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "../../include/cap4d_b200.h"
 #include "exec_common.h"
@@ -31,7 +34,7 @@ namespace {
 
 // GEGLU interleave (attention.py:68-75): rows [0,inner) = x, [inner,2*inner) = gate ->
 // packed row (r/32)*64 + half*32 + r%32
-__global__ void pack_geglu_kernel(const float* w, const float* b, int inner, int K, bf16* wout, float* bout) {
+__global__ void pack_geglu_kernel(const float* w, const float* b, int inner, int K, bf16* wout, float* bout, int f16) {
   const size_t total = static_cast<size_t>(2) * inner * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -39,9 +42,26 @@ __global__ void pack_geglu_kernel(const float* w, const float* b, int inner, int
     const int half = row >= static_cast<size_t>(inner);
     const size_t r = row - static_cast<size_t>(half) * inner;
     const size_t prow = (r / 32) * 64 + half * 32 + (r % 32);
-    wout[prow * K + c] = __float2bfloat16(w[i]);
+    if (f16) {
+      const __half hv = __float2half_rn(w[i]);
+      wout[prow * K + c] = *reinterpret_cast<const bf16*>(&hv);
+    } else {
+      wout[prow * K + c] = __float2bfloat16(w[i]);
+    }
     if (c == 0) bout[prow] = b[row];
   }
+}
+
+// max |x| into *out (non-negative floats order like their bit patterns)
+__global__ void absmax_kernel(const float* x, size_t n, float* out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = fabsf(x[i]);
+    m = (v > m || v != v) ? v : m;  // NaN propagates
+  }
+  if (m != m) m = __int_as_float(0x7f800000);
+  atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
 struct ResW {
@@ -108,6 +128,16 @@ struct Unet {
   // views (ref_mask == 1), so their outputs are x - z_input whatever the network computes for them.
   int ref_views = 0;
   int* d_violations = nullptr;  // broken n_ref_views promises seen by the output mix (device counter)
+  // Debug taps (cap4d_b200_unet_enable_taps): the fp32 NHWC activation after every block of the topology is copied
+  // into a slot of the workspace, for per-block error budgets against the oracle (tests/test_gpu_parity_budget.py).
+  bool taps_on = false;
+  struct TapInfo {
+    std::string name;
+    const float* ptr;
+    int64_t rows;
+    int C, n_img;
+  };
+  std::vector<TapInfo> taps;
   void* p_ws = nullptr;
   size_t p_ws_bytes = 0;
   struct CachedPlan {
@@ -350,14 +380,51 @@ struct Unet {
   }
   std::vector<std::string> consumed;
 
+  // Operand formats.  tcgen05 kind::f16 takes bf16 or fp16 operands (one format for both operands of an MMA: a
+  // mixed bf16 x fp16 descriptor faults on sm_100a).  fp16 has three more mantissa bits, and operand rounding IS the
+  // error budget of this path (bf16 everywhere: 7.7e-3 .. 1.03e-2 of the 1e-2 tolerance over seeds / timesteps,
+  // half of it from the weights alone, scripts/weight_rounding_error.py).  So every GEMM whose activation operand
+  // has a range bounded by construction - the output of a GroupNorm / LayerNorm (conv1, conv2, proj_in, QKV, FF1,
+  // the output conv) or the packed network input - runs fp16 x fp16; everything fed by an unnormalised tensor (raw
+  // residual stream into the skip / down / up convs, attention Q K V P and output, GEGLU output, FF2 / proj_out
+  // inputs) stays bf16 x bf16.  finalize() refuses weights that fp16 cannot hold.  CAP4D_OPERANDS=bf16: all bf16.
+  bool f16_ok = true;
+  void pack_as(bool f16) { set_weight_pack_f16(f16 && f16_ok); }
+
+  // every matrix / conv weight must be representable in fp16 (|w| <= 65504); checked on the device
+  bool weights_fit_f16() {
+    float* d_max = dev_alloc<float>(1, true);
+    if (!d_max) {
+      set_error("cudaMalloc failed");
+      return false;
+    }
+    for (const auto& kv : raw)
+      if (kv.second.shape.size() >= 2 && kv.second.numel > 0)
+        absmax_kernel<<<static_cast<unsigned>(std::min<size_t>(1024, (kv.second.numel + 255) / 256)), 256>>>(
+            kv.second.d, kv.second.numel, d_max);
+    float h = 0.f;
+    CUDA_OK(cudaMemcpy(&h, d_max, sizeof(float), cudaMemcpyDeviceToHost));
+    if (!(h <= 65504.f)) {
+      set_error("a weight exceeds the fp16 range (max |w| = " + std::to_string(h) + "); set CAP4D_OPERANDS=bf16");
+      return false;
+    }
+    return true;
+  }
+
   bool finalize() {
     if (finalized) return true;
+    if (const char* e = getenv("CAP4D_OPERANDS")) f16_ok = std::string(e) != "bf16";
+    struct PackGuard {  // the pack kernels read the target format from a thread-local switch
+      ~PackGuard() { set_weight_pack_f16(false); }
+    } pack_guard;
+    if (f16_ok && !weights_fit_f16()) return false;
     const int mc = cfg.model_channels;
     const RawTensor* t;
     // ---- conv_in + cond_linear fused into one [mc][kpad] matrix (mmdm_unet.py:92-107)
     {
       w_in = dev_alloc<bf16>(static_cast<size_t>(mc) * kpad_in, true);
       b_in = dev_alloc<float>(mc);
+      pack_as(true);
       if (!get("input_blocks.0.0.weight", static_cast<size_t>(mc) * cfg.in_channels * 9, &t)) return false;
       CUDA_OK(launch_pack_conv_weight(t->d, mc, cfg.in_channels, 3, 3, w_in, kpad_in, 0, 0));
       consumed.push_back("input_blocks.0.0.weight");
@@ -392,6 +459,7 @@ struct Unet {
         set_error("cudaMalloc failed");
         return false;
       }
+      pack_as(true);
       CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cin, 3, 3, r.w1, 9 * r.cin, 0, 0));
       consumed.push_back(p + "in_layers.2.weight");
       const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
@@ -402,6 +470,7 @@ struct Unet {
         set_error("cudaMalloc failed");
         return false;
       }
+      pack_as(!r.skip);  // the fused 1x1 skip conv reads the raw residual stream: that MMA stays bf16
       CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cout, 3, 3, r.w2, k2, 0, 0));
       consumed.push_back(p + "out_layers.3.weight");
       float *bo, *bs = nullptr;
@@ -433,10 +502,13 @@ struct Unet {
           !fp(tb + "norm3.weight", C, &w.ln3_g) || !fp(tb + "norm3.bias", C, &w.ln3_b) ||
           !fp(tb + "attn1.to_out.0.bias", C, &w.bo) || !fp(tb + "ff.net.2.bias", C, &w.bff2))
         return false;
-      if (!pack_linear(p + "proj_in.weight", C, C, &w.wpi) || !pack_linear(p + "proj_out.weight", C, C, &w.wpo) ||
-          !pack_linear(tb + "attn1.to_out.0.weight", C, C, &w.wo) ||
+      pack_as(true);   // proj_in reads a GroupNorm output
+      if (!pack_linear(p + "proj_in.weight", C, C, &w.wpi)) return false;
+      pack_as(false);  // proj_out / to_out / FF2 read unnormalised activations
+      if (!pack_linear(p + "proj_out.weight", C, C, &w.wpo) || !pack_linear(tb + "attn1.to_out.0.weight", C, C, &w.wo) ||
           !pack_linear(tb + "ff.net.2.weight", C, 4 * C, &w.wff2))
         return false;
+      pack_as(true);   // QKV and FF1 read LayerNorm outputs
       // fused QKV [3C][C] (attention.py:168-170, no bias)
       w.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
       if (!w.wqkv) {
@@ -460,10 +532,11 @@ struct Unet {
         set_error("cudaMalloc failed");
         return false;
       }
-      pack_geglu_kernel<<<sm_count() * 8, 256>>>(t->d, tbias->d, 4 * C, C, w.wff1, w.bff1);
+      pack_geglu_kernel<<<sm_count() * 8, 256>>>(t->d, tbias->d, 4 * C, C, w.wff1, w.bff1, f16_ok ? 1 : 0);
       consumed.push_back(tb + "ff.net.0.proj.weight");
     }
-    // ---- down / up convs
+    // ---- down / up convs (inputs: the raw residual stream -> bf16)
+    pack_as(false);
     for (int pass = 0; pass < 2; ++pass) {
       for (ConvW& c : (pass == 0 ? down : up)) {
         if (!get(c.prefix + "weight", static_cast<size_t>(c.cout) * c.cin * 9, &t)) return false;
@@ -488,6 +561,7 @@ struct Unet {
         set_error("out_channels > 32 is not implemented");
         return false;
       }
+      pack_as(true);
       w_out = dev_alloc<bf16>(static_cast<size_t>(32) * 9 * mc, true);
       b_out = dev_alloc<float>(32, true);
       if (!get("out.2.weight", static_cast<size_t>(cfg.out_channels) * mc * 9, &t)) return false;
@@ -542,7 +616,8 @@ struct Unet {
     }
   };
 
-  bool add_gemm_op(PlanCtx& c, int cls, const GemmPlan& plan, double exec_flops = -1) {
+  // f16: both operands of this GEMM are stored as fp16 (see "Operand formats" above)
+  bool add_gemm_op(PlanCtx& c, int cls, const GemmPlan& plan, bool f16, double exec_flops = -1) {
     Op op;
     op.cls = cls;
     op.launches = 1;
@@ -550,13 +625,14 @@ struct Unet {
     op.exec_flops = exec_flops;
     op.bytes = 0;
     GemmPlan copy = plan;
+    copy.p.a_f16 = copy.p.b_f16 = (f16 && f16_ok) ? 1 : 0;
     op.run = [copy](cudaStream_t s) { return launch_gemm(copy, s); };
     c.ops->push_back(op);
     return true;
   }
 
   bool op_gn(PlanCtx& c, const Buf& x1, const Buf* x2, int hw, const float* g, const float* b, float eps, int silu,
-             const Buf& out, const Buf* raw_out) {
+             const Buf& out, const Buf* raw_out, bool out_f16) {
     if (c.dry) return true;
     const float* p1 = c.ptr<float>(x1);
     const float* p2 = x2 ? c.ptr<float>(*x2) : nullptr;
@@ -567,6 +643,7 @@ struct Unet {
     const int n_img = c.n_img;
     // once compact, x1 holds the generated views only while a skip tensor x2 still holds every view
     const int x2G = (c.compact && x2 != nullptr) ? c.G : 0, x2V = c.V, x2R = c.R, n_layout = c.B * c.V;
+    const int f16 = (out_f16 && f16_ok) ? 1 : 0;
     Op op;
     op.cls = CLS_GN;
     op.launches = 1;
@@ -574,13 +651,13 @@ struct Unet {
     op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
     op.run = [=](cudaStream_t s) {
       return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s, x2G, x2V, x2R,
-                              n_layout);
+                              n_layout, f16);
     };
     c.ops->push_back(op);
     return true;
   }
 
-  bool op_ln(PlanCtx& c, const Buf& x, const float* g, const float* b, const Buf& out) {
+  bool op_ln(PlanCtx& c, const Buf& x, const float* g, const float* b, const Buf& out) {  // output: fp16 (f16_ok)
     if (c.dry) return true;
     const float* px = c.ptr<float>(x);
     bf16* po = c.ptr<bf16>(out);
@@ -590,7 +667,8 @@ struct Unet {
     op.launches = 1;
     op.flops = 0;
     op.bytes = static_cast<double>(M) * C * 6;
-    op.run = [=](cudaStream_t s) { return launch_layernorm(px, M, C, g, b, 1e-5f, po, s); };
+    const int f16 = f16_ok ? 1 : 0;
+    op.run = [=](cudaStream_t s) { return launch_layernorm(px, M, C, g, b, 1e-5f, po, s, f16); };
     c.ops->push_back(op);
     return true;
   }
@@ -605,7 +683,7 @@ struct Unet {
     }
     Buf a1 = c.alloc(M, cin, 2), xb;
     if (r.skip) xb = c.alloc(M, cin, 2);
-    if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr)) return false;
+    if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr, true)) return false;
     Buf h = c.alloc(M, r.cout, 4);
     ConvGeom g{c.n_img, H, W, 9, 1};
     if (!c.dry) {
@@ -613,11 +691,11 @@ struct Unet {
       if (!make_conv_plan(&p, c.ptr<bf16>(a1), g, cin, nullptr, 0, r.w1, r.cout, OUT_F32, c.ptr<float>(h), r.cout,
                           r.b1, c.emb_all + r.emb_off, hw, n_all, nullptr, 0))
         return false;
-      add_gemm_op(c, CLS_CONV, p);
+      add_gemm_op(c, CLS_CONV, p, true);
     }
     c.release(a1);
     Buf a2 = c.alloc(M, r.cout, 2);
-    if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr)) return false;
+    if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr, !r.skip)) return false;
     c.release(h);
     *out = c.alloc(M, r.cout, 4);
     if (!c.dry) {
@@ -626,7 +704,7 @@ struct Unet {
       if (!make_conv_plan(&p, c.ptr<bf16>(a2), g, r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? cin : 0, r.w2,
                           r.cout, OUT_F32, c.ptr<float>(*out), r.cout, r.b2, nullptr, 1, 0, residual, r.cout))
         return false;
-      add_gemm_op(c, CLS_CONV, p);
+      add_gemm_op(c, CLS_CONV, p, !r.skip);
     }
     c.release(a2);
     c.release(xb);
@@ -637,23 +715,23 @@ struct Unet {
   bool plan_tf(PlanCtx& c, const TfW& w, const Buf& x, int H, int W, Buf* out) {
     const int M = x.M, C = w.C, hw = H * W;
     Buf a = c.alloc(M, C, 2);
-    if (!op_gn(c, x, nullptr, hw, w.gn_g, w.gn_b, 1e-6f, 0, a, nullptr)) return false;
+    if (!op_gn(c, x, nullptr, hw, w.gn_g, w.gn_b, 1e-6f, 0, a, nullptr, true)) return false;
     Buf t0 = c.alloc(M, C, 4);
     auto gemm = [&](const Buf& A, int K, const bf16* Wt, int N, int mode, const Buf& o, int ldo, const float* bias,
-                    const float* residual) -> bool {
+                    const float* residual, bool f16) -> bool {
       if (c.dry) return true;
       GemmPlan p;
       if (!make_gemm_plan(&p, c.ptr<bf16>(A), M, K, nullptr, 0, Wt, N, mode, c.base + o.off, ldo, bias, nullptr, 1, 0,
                           residual, C))
         return false;
-      return add_gemm_op(c, CLS_LINEAR, p);
+      return add_gemm_op(c, CLS_LINEAR, p, f16);
     };
-    if (!gemm(a, C, w.wpi, C, OUT_F32, t0, C, w.bpi, nullptr)) return false;
+    if (!gemm(a, C, w.wpi, C, OUT_F32, t0, C, w.bpi, nullptr, true)) return false;
     c.release(a);
     Buf n1 = c.alloc(M, C, 2);
     if (!op_ln(c, t0, w.ln1_g, w.ln1_b, n1)) return false;
     Buf qkv = c.alloc(M, 3 * C, 2);
-    if (!gemm(n1, C, w.wqkv, 3 * C, OUT_BF16, qkv, 3 * C, nullptr, nullptr)) return false;
+    if (!gemm(n1, C, w.wqkv, 3 * C, OUT_BF16, qkv, 3 * C, nullptr, nullptr, true)) return false;
     c.release(n1);
     Buf o = c.alloc(M, C, 2);
     if (!c.dry) {
@@ -670,20 +748,20 @@ struct Unet {
     }
     c.release(qkv);
     Buf t1 = c.alloc(M, C, 4);
-    if (!gemm(o, C, w.wo, C, OUT_F32, t1, C, w.bo, c.dry ? nullptr : c.ptr<float>(t0))) return false;
+    if (!gemm(o, C, w.wo, C, OUT_F32, t1, C, w.bo, c.dry ? nullptr : c.ptr<float>(t0), false)) return false;
     c.release(o);
     c.release(t0);
     Buf n3 = c.alloc(M, C, 2);
     if (!op_ln(c, t1, w.ln3_g, w.ln3_b, n3)) return false;
     Buf gg = c.alloc(M, 4 * C, 2);
-    if (!gemm(n3, C, w.wff1, 8 * C, OUT_GEGLU_BF16, gg, 4 * C, w.bff1, nullptr)) return false;
+    if (!gemm(n3, C, w.wff1, 8 * C, OUT_GEGLU_BF16, gg, 4 * C, w.bff1, nullptr, true)) return false;
     c.release(n3);
     Buf t2 = c.alloc(M, C, 2);
-    if (!gemm(gg, 4 * C, w.wff2, C, OUT_BF16, t2, C, w.bff2, c.dry ? nullptr : c.ptr<float>(t1))) return false;
+    if (!gemm(gg, 4 * C, w.wff2, C, OUT_BF16, t2, C, w.bff2, c.dry ? nullptr : c.ptr<float>(t1), false)) return false;
     c.release(gg);
     c.release(t1);
     *out = c.alloc(M, C, 4);
-    if (!gemm(t2, C, w.wpo, C, OUT_F32, *out, C, w.bpo, c.dry ? nullptr : c.ptr<float>(x))) return false;
+    if (!gemm(t2, C, w.wpo, C, OUT_F32, *out, C, w.bpo, c.dry ? nullptr : c.ptr<float>(x), false)) return false;
     c.release(t2);
     return true;
   }
@@ -709,7 +787,7 @@ struct Unet {
       if (!make_conv_plan(&p, ppp, g, C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1,
                           0, nullptr, 0))
         return false;
-      add_gemm_op(c, CLS_CONV, p);
+      add_gemm_op(c, CLS_CONV, p, false);
     }
     c.release(pp);
     return true;
@@ -742,7 +820,7 @@ struct Unet {
           return false;
         const double executed = p.flops;                            // 4 taps on the low-resolution grid
         p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C;  // algorithmic: the un-folded conv's share
-        add_gemm_op(c, CLS_CONV, p, executed);
+        add_gemm_op(c, CLS_CONV, p, false, executed);
       }
     }
     c.release(xb);
@@ -775,6 +853,23 @@ struct Unet {
     c.n_img = c.B * c.G;
     c.emb_all = c.emb_gen;
     return true;
+  }
+
+  void add_tap(PlanCtx& c, const std::string& name, const Buf& cur) {
+    if (!taps_on) return;
+    Buf slot = c.alloc(cur.M, cur.C, 4);  // never released: lives until the next forward
+    if (c.dry) return;
+    const float* src = c.ptr<float>(cur);
+    float* dst = c.ptr<float>(slot);
+    const size_t bytes = cur.bytes;
+    taps.push_back({name, dst, cur.M, cur.C, c.n_img});
+    Op op;
+    op.cls = CLS_OTHER;
+    op.launches = 0;
+    op.flops = 0;
+    op.bytes = 2.0 * bytes;
+    op.run = [=](cudaStream_t s) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s); };
+    c.ops->push_back(op);
   }
 
   bool plan_block(PlanCtx& c, const Block& blk, Buf x, const Buf* skip, int* H, int* W, Buf* out,
@@ -888,7 +983,7 @@ struct Unet {
     if (!c.dry) {
       IoPtrs* iop = &io;
       bf16* pa0 = c.ptr<bf16>(a0);
-      const int cin = cfg.in_channels, cc = cfg.condition_channels, kp = kpad_in;
+      const int cin = cfg.in_channels, cc = cfg.condition_channels, kp = kpad_in, in_f16 = f16_ok ? 1 : 0;
       {
         Op op;
         op.cls = CLS_OTHER;
@@ -896,7 +991,7 @@ struct Unet {
         op.flops = 0;
         op.bytes = static_cast<double>(M0) * (kp * 2 + cc * 4 + cin * 8);
         op.run = [=](cudaStream_t s) {
-          return launch_input_pack(iop->x, iop->z, iop->mask, iop->pos, n_img, cin, H, W, cc, kp, pa0, s);
+          return launch_input_pack(iop->x, iop->z, iop->mask, iop->pos, n_img, cin, H, W, cc, kp, pa0, s, in_f16);
         };
         c.ops->push_back(op);
       }
@@ -931,7 +1026,7 @@ struct Unet {
       if (!make_gemm_plan(&p, pa0, M0, kp, nullptr, 0, w_in, mc, OUT_F32, c.ptr<float>(h), mc, b_in, nullptr, 1, 0,
                           nullptr, 0))
         return false;
-      add_gemm_op(c, CLS_LINEAR, p);
+      add_gemm_op(c, CLS_LINEAR, p, true);
     }
     c.release(a0);
     // ---- down path
@@ -939,6 +1034,8 @@ struct Unet {
     hs.push_back(h);
     int curH = H, curW = W;
     Buf cur = h;
+    if (!c.dry) taps.clear();
+    add_tap(c, "input_blocks.0", h);
     for (size_t bi = 1; bi < input_blocks.size(); ++bi) {
       Buf nxt;
       // the block input is also a skip tensor: do not let plan_block release it
@@ -947,6 +1044,7 @@ struct Unet {
       if (!plan_block(c, input_blocks[bi], keep, nullptr, &curH, &curW, &nxt)) return false;
       hs.push_back(nxt);
       cur = nxt;
+      add_tap(c, "input_blocks." + std::to_string(bi), cur);
     }
     // ---- middle
     {
@@ -955,6 +1053,7 @@ struct Unet {
       Buf nxt;
       if (!plan_block(c, middle, keep, nullptr, &curH, &curW, &nxt)) return false;
       cur = nxt;  // owned
+      add_tap(c, "middle_block", cur);
     }
     // ---- up path
     for (size_t bi = 0; bi < output_blocks.size(); ++bi) {
@@ -965,11 +1064,12 @@ struct Unet {
       if (!plan_block(c, output_blocks[bi], cur, &skip, &curH, &curW, &nxt, compact_after)) return false;
       c.release(skip);
       cur = nxt;
+      add_tap(c, "output_blocks." + std::to_string(bi), cur);
     }
     // ---- out (on the generated views only once compact)
     const int Mo = c.n_img * H * W;
     Buf a = c.alloc(Mo, mc, 2);
-    if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr)) return false;
+    if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr, true)) return false;
     c.release(cur);
     Buf o32 = c.alloc(Mo, 32, 4);
     if (!c.dry) {
@@ -978,7 +1078,7 @@ struct Unet {
       if (!make_conv_plan(&p, c.ptr<bf16>(a), g, mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
                           nullptr, 1, 0, nullptr, 0))
         return false;
-      add_gemm_op(c, CLS_CONV, p);
+      add_gemm_op(c, CLS_CONV, p, true);
       IoPtrs* iop = &io;
       const float* po = c.ptr<float>(o32);
       const int cout = cfg.out_channels;
@@ -1282,6 +1382,53 @@ int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views) {
   return 0;
 }
 
+int cap4d_b200_unet_enable_taps(void* handle, int on) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  if (u->taps_on != (on != 0)) {  // the taps are part of the launch plan: drop every plan
+    u->taps_on = on != 0;
+    u->ops.clear();
+    u->cache.clear();
+    u->taps.clear();
+    u->pB = u->pV = u->pH = u->pW = 0;
+  }
+  return 0;
+}
+
+int cap4d_b200_unet_num_taps(void* handle, int* n) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || n == nullptr) {
+    set_error("null argument");
+    return 1;
+  }
+  *n = static_cast<int>(u->taps.size());
+  return 0;
+}
+
+int cap4d_b200_unet_tap_info(void* handle, int index, char* name, int name_capacity, const float** data, int64_t* rows,
+                             int* channels, int* n_img) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr || name == nullptr || data == nullptr || rows == nullptr || channels == nullptr || n_img == nullptr ||
+      index < 0 || index >= static_cast<int>(u->taps.size())) {
+    set_error("tap_info: bad argument");
+    return 1;
+  }
+  const Unet::TapInfo& t = u->taps[index];
+  if (static_cast<int>(t.name.size()) + 1 > name_capacity) {
+    set_error("name buffer too small");
+    return 1;
+  }
+  std::strcpy(name, t.name.c_str());
+  *data = t.ptr;
+  *rows = t.rows;
+  *channels = t.C;
+  *n_img = t.n_img;
+  return 0;
+}
+
 int cap4d_b200_unet_ref_view_violations(void* handle, int* n) {
   Unet* u = static_cast<Unet*>(handle);
   if (u == nullptr || n == nullptr) {
@@ -1420,6 +1567,19 @@ int cap4d_b200_gemm_bf16(const uint16_t* A, const uint16_t* Wt, int M, int N, in
   if (!make_gemm_plan(&p, reinterpret_cast<const bf16*>(A), M, K, nullptr, 0, reinterpret_cast<const bf16*>(Wt), N,
                       out_mode, out, ldo, bias, nullptr, 1, 0, residual, ldo))
     return 10;
+  return run_timed([&](cudaStream_t s) { return launch_gemm(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
+}
+
+int cap4d_b200_gemm_mixed(const uint16_t* A, const uint16_t* Wt, int M, int N, int K, int a_f16, int b_f16,
+                          const float* bias, const float* residual, void* out, int out_mode, void* stream,
+                          float* ms_out, int iters) {
+  GemmPlan p;
+  const int ldo = (out_mode == OUT_GEGLU_BF16) ? N / 2 : N;
+  if (!make_gemm_plan(&p, reinterpret_cast<const bf16*>(A), M, K, nullptr, 0, reinterpret_cast<const bf16*>(Wt), N,
+                      out_mode, out, ldo, bias, nullptr, 1, 0, residual, ldo))
+    return 10;
+  p.p.a_f16 = a_f16 ? 1 : 0;
+  p.p.b_f16 = b_f16 ? 1 : 0;
   return run_timed([&](cudaStream_t s) { return launch_gemm(p, s); }, static_cast<cudaStream_t>(stream), ms_out, iters);
 }
 

@@ -46,6 +46,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out_mode: i
     return (out, ms.value) if time_iters else out
 
 
+def gemm_mixed(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out_mode: int = OUT_F32, time_iters: int = 0):
+    """gemm() with each operand either bf16 or fp16 (the U-Net executor's combination is bf16 activations x fp16
+    weights); the formats are taken from the tensors' dtypes."""
+    _check_cuda(a, w, bias, residual)
+    fmts = {torch.bfloat16: 0, torch.float16: 1}
+    assert a.dtype in fmts and w.dtype in fmts and a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if out_mode == OUT_GEGLU else N
+    out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_mode == OUT_F32 else torch.bfloat16)
+    ms = ctypes.c_float(0)
+    lib = _lib.load()
+    _lib.check(
+        lib.cap4d_b200_gemm_mixed(_ptr(a), _ptr(w), M, N, K, fmts[a.dtype], fmts[w.dtype], _ptr(bias), _ptr(residual),
+                                  _ptr(out), out_mode, _stream(a.device), ctypes.byref(ms) if time_iters else None,
+                                  max(1, time_iters)),
+        "gemm_mixed",
+    )
+    return (out, ms.value) if time_iters else out
+
+
 def conv3x3(a_nhwc: torch.Tensor, w_packed: torch.Tensor, n_img: int, H_out: int, W_out: int, stride: int = 1,
             bias=None, rowbias=None, residual=None, time_iters: int = 0):
     """3x3 conv, pad 1.  a_nhwc: bf16 [n_img,H,W,Cin] (stride 2: parity planes [4,n_img,H/2,W/2,Cin]);

@@ -338,6 +338,36 @@ class B200MMDMUnet(torch.nn.Module):
                     "unet_forward",
                 )
 
+    def enable_taps(self, on: bool = True) -> None:
+        """Debug: keep the activation after every block of the next forwards (see taps())."""
+        self._ensure_built()
+        _lib.check(self._lib.cap4d_b200_unet_enable_taps(self._handle, int(bool(on))), "enable_taps")
+        self._ws = {}  # the workspace size depends on it
+
+    def taps(self, H: int, W: int) -> Dict[str, torch.Tensor]:
+        """After a forward with taps enabled: {"input_blocks.3": [n_img, C, h, w] fp32, ...} (copies), in the
+        reference's module naming and NCHW layout.  H, W: the latent size of that forward."""
+        n = ctypes.c_int()
+        _lib.check(self._lib.cap4d_b200_unet_num_taps(self._handle, ctypes.byref(n)), "num_taps")
+        out = {}
+        name = ctypes.create_string_buffer(128)
+        ptr, rows, ch, nimg = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+        with torch.cuda.device(self._device):
+            torch.cuda.synchronize(self._device)
+            for i in range(n.value):
+                _lib.check(self._lib.cap4d_b200_unet_tap_info(self._handle, i, name, 128, ctypes.byref(ptr),
+                                                              ctypes.byref(rows), ctypes.byref(ch), ctypes.byref(nimg)),
+                           "tap_info")
+                ws = next(w for w in self._ws.values()
+                          if w.data_ptr() <= ptr.value < w.data_ptr() + w.numel())
+                off = ptr.value - ws.data_ptr()
+                flat = ws[off: off + rows.value * ch.value * 4].view(torch.float32)
+                hw = rows.value // nimg.value
+                scale = int(round((H * W / hw) ** 0.5))
+                t = flat.view(nimg.value, H // scale, W // scale, ch.value).permute(0, 3, 1, 2).contiguous()
+                out[name.value.decode()] = t
+        return out
+
     def collect_timings(self):
         """Per-class ms summed over the recorded forwards since the last call -> ({class: ms}, n_forwards)."""
         self._ensure_built()

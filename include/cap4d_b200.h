@@ -107,6 +107,17 @@ int cap4d_b200_unet_forward_timed(void* handle, const float* x, const int64_t* t
 
 int cap4d_b200_unet_collect_timings(void* handle, float* class_ms, int* n_runs);
 
+/* Debug taps (no reference counterpart; the reference would use forward hooks): with taps enabled every forward
+ * also keeps the fp32 activation after each block of the topology - "input_blocks.<i>", "middle_block",
+ * "output_blocks.<i>", the module names of openaimodel.py:544-774 - in the workspace (which therefore grows).
+ * tap_info, valid after a forward, returns a DEVICE pointer to the token-major (NHWC) tensor [rows][channels] of tap
+ * `index`; n_img is the image count it covers (fewer than B*V once the reference views were dropped, see
+ * set_ref_views).  Enabling / disabling drops the cached launch plans. */
+int cap4d_b200_unet_enable_taps(void* handle, int on);
+int cap4d_b200_unet_num_taps(void* handle, int* n);
+int cap4d_b200_unet_tap_info(void* handle, int index, char* name, int name_capacity, const float** data, int64_t* rows,
+                             int* channels, int* n_img);
+
 int cap4d_b200_unet_destroy(void* handle);
 
 /* ---- sampler update: replaces cap4d/mmdm/sampler.py:205-208 + 215-231 ----------------------
@@ -176,6 +187,12 @@ int cap4d_b200_sampler_unpack(float* latents, const float* recv, const int64_t* 
  * out_mode 0: fp32, 1: bf16, 2: GEGLU (attention.py:68-75; W/bias rows interleaved [x32|gate32]). */
 int cap4d_b200_gemm_bf16(const uint16_t* A, const uint16_t* Wt, int M, int N, int K, const float* bias,
                          const float* residual, void* out, int out_mode, void* stream, float* ms_out, int iters);
+
+/* The same GEMM with the 16-bit storage format of each operand chosen separately (0 = bf16, 1 = fp16): the U-Net
+ * executor keeps activations in bf16 and stores the weights as fp16 ("operand formats"). */
+int cap4d_b200_gemm_mixed(const uint16_t* A, const uint16_t* Wt, int M, int N, int K, int a_f16, int b_f16,
+                          const float* bias, const float* residual, void* out, int out_mode, void* stream,
+                          float* ms_out, int iters);
 
 /* nn.Conv2d(k=3, pad=1, stride 1|2) on NHWC bf16 (stride 2: parity planes); weights [Cout][9*Cin]
  * tap-major; optional rowbias[n_img][Cout] (ResBlock emb_out, openaimodel.py:265-274). */

@@ -50,6 +50,21 @@ def test_gemm_f32(ops, cuda_device, M, N, K):
     assert _rel(out, ref) < 2e-5  # fp32 accumulation of exact bf16 products vs fp64
 
 
+@pytest.mark.parametrize("a_dt,w_dt", [(torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)])
+def test_gemm_operand_formats(ops, cuda_device, a_dt, w_dt):
+    """The executor runs fp16 x fp16 where a norm bounds the activation's range and bf16 x bf16 elsewhere (a mixed
+    bf16 x fp16 descriptor faults on sm_100a, which is why there is no such case here).  Exact products of the stored
+    values, fp32 accumulation: the same tolerance for both formats."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 384, 320, 1280
+    a = torch.randn(M, K, generator=g).to(cuda_device).to(a_dt)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device).to(w_dt)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    out = ops.gemm_mixed(a, w, bias=bias)
+    ref = a.double() @ w.double().t() + bias.double()
+    assert _rel(out, ref) < 2e-5
+
+
 def test_gemm_no_epilogue_and_bf16_out(ops, cuda_device):
     g = torch.Generator().manual_seed(1)
     a = torch.randn(512, 256, generator=g).to(cuda_device).to(torch.bfloat16)
