@@ -64,6 +64,7 @@ SIGNATURES = {
     "cap4d_b200_unet_num_params": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "cap4d_b200_unet_finalize": (c_int, [c_void_p]),
+    "cap4d_b200_unet_set_precision": (c_int, [c_void_p, c_int]),
     "cap4d_b200_unet_set_ref_views": (c_int, [c_void_p, c_int]),
     "cap4d_b200_unet_ref_view_violations": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_vae_create": (c_int, [POINTER(VaeConfig), POINTER(c_void_p)]),
@@ -87,6 +88,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
          c_size_t, c_void_p],
     ),
+    "cap4d_b200_unet_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
     "cap4d_b200_unet_num_launches": (c_int, [c_void_p, POINTER(c_int)]),
     "cap4d_b200_unet_class_stats": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int)]),
     "cap4d_b200_unet_class_exec_flops": (c_int, [c_void_p, POINTER(c_double)]),

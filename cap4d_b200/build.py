@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcap4d_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu", "vae_exec.cu", "cond_map.cu", "sampler_plane.cu"]
+SOURCES = ["gemm_tc.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "unet_exec.cu", "vae_exec.cu", "cond_map.cu", "sampler_plane.cu", "precise.cu"]
 HEADERS = ["ptx.cuh", "kernels.h", "exec_common.h", os.path.join("..", "..", "include", "cap4d_b200.h")]
 
 # cond_map.cu decides triangle coverage with the same fp32 operations as its CPU restatement: no FMA contraction

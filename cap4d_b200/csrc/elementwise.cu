@@ -39,7 +39,9 @@ __global__ void input_pack_kernel(const float* __restrict__ x, const float* __re
     } else if (k < 9 * cin + cc) {
       v = pos[pix * cc + (k - 9 * cin)];
     }
-    if (out_f16) {
+    if (out_f16 == 2) {
+      reinterpret_cast<float*>(out)[i] = v;
+    } else if (out_f16) {
       const __half hv = __float2half_rn(v);
       out[i] = *reinterpret_cast<const bf16*>(&hv);
     } else {
@@ -95,7 +97,7 @@ __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __re
 
 // ---- fp32 NHWC -> bf16 parity planes for the stride-2 conv (openaimodel.py:150-153) ------------
 __global__ void parity_split_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
-                                    bf16* __restrict__ out) {
+                                    bf16* __restrict__ out, int out_f32) {
   const int quads = C >> 2;
   const size_t total = static_cast<size_t>(n_img) * H * W * quads;
   const int H2 = H >> 1, W2 = W >> 1;
@@ -109,7 +111,10 @@ __global__ void parity_split_kernel(const float* __restrict__ x, int n_img, int 
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     const int plane = (yy & 1) * 2 + (xx & 1);
     const size_t o = (((static_cast<size_t>(plane) * n_img + n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * C + qd * 4;
-    *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    if (out_f32)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = v;
+    else
+      *reinterpret_cast<uint2*>(out + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
 
@@ -314,13 +319,17 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ src, int ld, int 
 }
 
 // ---- weight repacks ---------------------------------------------------------------------------
-// 16-bit storage of a weight: bf16, or the fp16 bit pattern in the same 2 bytes (kernels.h: set_weight_pack_f16)
-__device__ __forceinline__ bf16 w16(float v, int f16) {
-  if (f16) {
+// storage of a repacked weight (kernels.h: set_weight_pack_format): 0 bf16, 1 the fp16 bit pattern in the same two
+// bytes, 2 fp32 (out then points at floats: the fp32-accuracy mode splits them afterwards, precise.cu)
+__device__ __forceinline__ void store_w(bf16* out, size_t idx, float v, int fmt) {
+  if (fmt == 2) {
+    reinterpret_cast<float*>(out)[idx] = v;
+  } else if (fmt == 1) {
     const __half h = __float2half_rn(v);
-    return *reinterpret_cast<const bf16*>(&h);
+    out[idx] = *reinterpret_cast<const bf16*>(&h);
+  } else {
+    out[idx] = __float2bfloat16(v);
   }
-  return __float2bfloat16(v);
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW,
@@ -333,7 +342,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
     const int tap = static_cast<int>((idx / I) % (KH * KW));
     const size_t o = idx / (static_cast<size_t>(I) * KH * KW);
     const float v = w[(o * I + i) * KH * KW + tap];
-    out[o * ldk + k_offset + static_cast<size_t>(tap) * I + i] = w16(v, f16);
+    store_w(out, o * ldk + k_offset + static_cast<size_t>(tap) * I + i, v, f16);
   }
 }
 
@@ -343,7 +352,7 @@ __global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int co
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t r = idx / cols, c = idx % cols;
-    out[(row_offset + r) * ldk + k_offset + c] = w16(w[idx], f16);
+    store_w(out, (row_offset + r) * ldk + k_offset + c, w[idx], f16);
   }
 }
 
@@ -366,7 +375,7 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int O, in
     float acc = 0.f;
     for (int ky = ky0; ky <= ky1; ++ky)
       for (int kx = kx0; kx <= kx1; ++kx) acc += w[((o * I + i) * 3 + ky) * 3 + kx];
-    out[idx] = w16(acc, f16);
+    store_w(out, idx, acc, f16);
   }
 }
 
@@ -453,9 +462,9 @@ cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int 
 }
 
 cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, int C, bf16* out,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, int out_f32) {
   const size_t total = static_cast<size_t>(n_img) * H * W * (C / 4);
-  parity_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, H, W, C, out);
+  parity_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, n_img, H, W, C, out, out_f32);
   return cudaGetLastError();
 }
 
@@ -488,20 +497,21 @@ cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int e
   return cudaGetLastError();
 }
 
-static thread_local bool g_pack_f16 = false;
-void set_weight_pack_f16(bool f16) { g_pack_f16 = f16; }
-bool weight_pack_f16() { return g_pack_f16; }
+static thread_local int g_pack_fmt = 0;
+void set_weight_pack_format(int fmt) { g_pack_fmt = fmt; }
+int weight_pack_format() { return g_pack_fmt; }
+void set_weight_pack_f16(bool f16) { g_pack_fmt = f16 ? 1 : 0; }
 
 cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
                                     int k_offset, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(O) * I * KH * KW;
-  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset, weight_pack_f16() ? 1 : 0);
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, KH, KW, out, ldk, k_offset, weight_pack_format());
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(16) * O * I;
-  pack_upconv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, out, weight_pack_f16() ? 1 : 0);
+  pack_upconv_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w_oihw, O, I, out, weight_pack_format());
   return cudaGetLastError();
 }
 
@@ -518,7 +528,7 @@ cudaError_t launch_pack_matrix(const float* w, int rows, int cols, bf16* out, in
                                cudaStream_t stream) {
   const size_t total = static_cast<size_t>(rows) * cols;
   pack_matrix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, rows, cols, out, ldk, k_offset, row_offset,
-                                                               weight_pack_f16() ? 1 : 0);
+                                                               weight_pack_format());
   return cudaGetLastError();
 }
 

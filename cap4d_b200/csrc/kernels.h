@@ -129,7 +129,8 @@ enum { GN_MAX_CHUNKS = 128 };
 cudaError_t launch_groupnorm(const float* x1, int C1, const float* x2, int C2, int n_img, int hw, const float* gamma,
                              const float* beta, float eps, int apply_silu, bf16* out, bf16* raw_out, float* partial,
                              cudaStream_t stream, int x2_G = 0, int x2_V = 0, int x2_R = 0, int n_img_layout = 0,
-                             int out_f16 = 0);  // out_f16: `out` is written as fp16 (raw_out stays bf16)
+                             int out_f16 = 0);  // out_f16: 1 = `out` is written as fp16 (raw_out stays bf16); 2 = out AND raw_out are
+                                                // fp32 and SiLU is exact (fp32-accuracy mode)
 size_t groupnorm_partial_bytes(int n_img);
 size_t groupnorm_sync_offset(int n_img);  // the bytes from here to the end must be zero before the first launch
 
@@ -156,7 +157,7 @@ cudaError_t launch_output_mix(const float* h, int ldh, const float* x, const flo
 cudaError_t launch_gather_views(const float* src, float* dst, int B, int V, int R, size_t per_img, cudaStream_t stream);
 // fp32 NHWC -> bf16 parity planes [4][n_img][H/2][W/2][C] (plane = (y&1)*2 + (x&1))
 cudaError_t launch_parity_split_bf16(const float* x, int n_img, int H, int W, int C, bf16* out,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, int out_f32 = 0);  // out_f32: planes stay fp32
 // timestep embedding + time_embed MLP + all ResBlock emb_layers (fp32):
 //   temb[n] = [cos(t f), sin(t f)] ; e = W2 silu(W1 temb + b1) + b2 ; out[n][:] = Wall silu(e) + ball
 cudaError_t launch_time_embed(const long long* t, int n_img, int model_ch, int emb_ch, const float* w1,
@@ -173,7 +174,9 @@ cudaError_t launch_cfg_ddim_update(float* latents, const float* eps, const long 
 // effect (thread-local; the executor sets it around its finalize): then the same buffers receive fp16 bit patterns
 // and the GEMM plans that read them carry b_f16 = 1.
 void set_weight_pack_f16(bool f16);
-bool weight_pack_f16();
+// general form: 0 bf16, 1 fp16, 2 fp32 (the output pointer then addresses floats; fp32-accuracy mode, precise.cu)
+void set_weight_pack_format(int fmt);
+int weight_pack_format();
 cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, int KW, bf16* out, int ldk,
                                     int k_offset, cudaStream_t stream);  // out[o][k_offset + (kh*KW+kw)*I + i]
 // nearest-2x-upsample + conv3x3 folded: out[phase][o][(a*2+b)*I + i] = sum of the 3x3 taps that fall on
@@ -181,6 +184,19 @@ cudaError_t launch_pack_conv_weight(const float* w_oihw, int O, int I, int KH, i
 cudaError_t launch_pack_upconv_weight(const float* w_oihw, int O, int I, bf16* out, cudaStream_t stream);
 // fp32 -> bf16 copy
 cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t stream);
+
+// ---- fp32-accuracy mode (precise.cu): exact bf16 x 3 operand splits and exact pointwise maths ----
+// x fp32 [rows][ldx] (columns [0, cols) in groups of group_width) -> out bf16 [rows][ld_out]: every group becomes six
+// group_width-wide segments, [l|h|m|m|h|h] (worder 0: activation side) or [h|l|m|h|m|h] (worder 1: weight side)
+cudaError_t launch_split6(const float* x, size_t rows, int cols, size_t ldx, int group_width, bf16* out, size_t ld_out,
+                          int worder, cudaStream_t stream);
+// out[r][c] = u[r][c] * gelu(u[r][inner + c]) (erf form, exact), u fp32 [rows][2 inner]
+cudaError_t launch_geglu_f32(const float* u, size_t rows, int inner, float* out, cudaStream_t stream);
+// in-place softmax(scale * s) over the rows of fp32 [rows][L]
+cudaError_t launch_softmax_rows_f32(float* s, int rows, int L, float scale, cudaStream_t stream);
+cudaError_t launch_transpose_f32(const float* src, size_t ld, int rows, int cols, float* dst, cudaStream_t stream);
+// attention on the fp32 fused qkv matrix [M][3C] -> fp32 [M][C] (same sequence convention as make_attn_plan)
+cudaError_t launch_attention_f32(const float* qkv, float* out, int M, int C, int L, float scale, cudaStream_t stream);
 
 // ---- VAE decode helpers (elementwise.cu) ----
 // z NCHW fp32 -> (z / scale) -> post_quant_conv -> im2col rows [n*H*W][kpad] bf16 for conv_in (3x3, pad 1)

@@ -286,6 +286,18 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
       float y1 = fmaf(v.y, a[qi][1], b[qi][1]);
       float y2 = fmaf(v.z, a[qi][2], b[qi][2]);
       float y3 = fmaf(v.w, a[qi][3], b[qi][3]);
+      if (out_f16 == 2) {
+        // fp32-accuracy mode: exact SiLU, fp32 out (split into bf16 triples by the next kernel, precise.cu)
+        if (apply_silu) {
+          y0 = y0 / (1.0f + expf(-y0));
+          y1 = y1 / (1.0f + expf(-y1));
+          y2 = y2 / (1.0f + expf(-y2));
+          y3 = y3 / (1.0f + expf(-y3));
+        }
+        __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * C + c), make_float4(y0, y1, y2, y3));
+        if (raw_out != nullptr) __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(raw_out) + row * C + c), v);
+        return;
+      }
       if (apply_silu) {
         y0 = silu_f(y0);
         y1 = silu_f(y1);
@@ -414,7 +426,10 @@ layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restr
       const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
       const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
       const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
-      *reinterpret_cast<uint2*>(orow + qd * 4) = make_uint2(pack16x2(y0, y1, out_f16), pack16x2(y2, y3, out_f16));
+      if (out_f16 == 2)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<size_t>(row) * C + qd * 4) = make_float4(y0, y1, y2, y3);
+      else
+        *reinterpret_cast<uint2*>(orow + qd * 4) = make_uint2(pack16x2(y0, y1, out_f16), pack16x2(y2, y3, out_f16));
     }
   }
 }

@@ -6,6 +6,7 @@
 // stream and bf16 as MMA operands; a forward is a fixed list of kernel launches on one stream with
 // every intermediate carved out of a caller-provided workspace (no allocation after planning).
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -369,14 +370,14 @@ struct Unet {
   bool pack_linear(const std::string& name, int rows, int cols, bf16** out) {
     const RawTensor* t;
     if (!get(name, static_cast<size_t>(rows) * cols, &t)) return false;
-    *out = dev_alloc<bf16>(static_cast<size_t>(rows) * cols);
+    *out = walloc(static_cast<size_t>(rows) * cols);
     if (!*out) {
       set_error("cudaMalloc failed for " + name);
       return false;
     }
     CUDA_OK(launch_pack_matrix(t->d, rows, cols, *out, cols, 0, 0, 0));
     consumed.push_back(name);
-    return true;
+    return split_weight(out, rows, cols, {{0, cols, cols}});
   }
   std::vector<std::string> consumed;
 
@@ -389,7 +390,32 @@ struct Unet {
   // residual stream into the skip / down / up convs, attention Q K V P and output, GEGLU output, FF2 / proj_out
   // inputs) stays bf16 x bf16.  finalize() refuses weights that fp16 cannot hold.  CAP4D_OPERANDS=bf16: all bf16.
   bool f16_ok = true;
-  void pack_as(bool f16) { set_weight_pack_f16(f16 && f16_ok); }
+  // fp32-accuracy mode (cap4d_b200_unet_set_precision, before finalize; see precise.cu): every MMA operand is the
+  // exact three-way bf16 split of an fp32 tensor laid out as six K segments, the pointwise maths is exact, attention
+  // runs in fp32.  kx() = how many times wider an operand is than the tensor it represents.
+  bool precise = false;
+  int kx() const { return precise ? 6 : 1; }
+  void pack_as(bool f16) { set_weight_pack_format(precise ? 2 : ((f16 && f16_ok) ? 1 : 0)); }
+  // weight buffer of n elements in the current pack format
+  bf16* walloc(size_t n, bool zero = false) { return dev_alloc<bf16>(precise ? 2 * n : n, zero); }
+  std::vector<void*> split_sources;  // fp32 repacked weights, freed once their splits exist
+  // precise mode: *w holds fp32 [rows][K] in the GEMM's K order -> bf16 [rows][6 K], weight-side segment order.
+  // parts: (first column, column count, segment width) - the K ranges that face different operand tensors
+  bool split_weight(bf16** w, int rows, int K, const std::vector<std::array<int, 3>>& parts) {
+    if (!precise) return true;
+    bf16* out = dev_alloc<bf16>(static_cast<size_t>(rows) * 6 * K);
+    if (!out) {
+      set_error("cudaMalloc failed (split weights)");
+      return false;
+    }
+    const float* src = reinterpret_cast<const float*>(*w);
+    for (const auto& pt : parts)
+      CUDA_OK(launch_split6(src + pt[0], rows, pt[1], K, pt[2], out + static_cast<size_t>(6) * pt[0],
+                            static_cast<size_t>(6) * K, 1, 0));
+    split_sources.push_back(*w);
+    *w = out;
+    return true;
+  }
 
   // every matrix / conv weight must be representable in fp16 (|w| <= 65504); checked on the device
   bool weights_fit_f16() {
@@ -417,12 +443,13 @@ struct Unet {
     struct PackGuard {  // the pack kernels read the target format from a thread-local switch
       ~PackGuard() { set_weight_pack_f16(false); }
     } pack_guard;
+    if (precise) f16_ok = false;  // the split operands are bf16 triples
     if (f16_ok && !weights_fit_f16()) return false;
     const int mc = cfg.model_channels;
     const RawTensor* t;
     // ---- conv_in + cond_linear fused into one [mc][kpad] matrix (mmdm_unet.py:92-107)
     {
-      w_in = dev_alloc<bf16>(static_cast<size_t>(mc) * kpad_in, true);
+      w_in = walloc(static_cast<size_t>(mc) * kpad_in, true);
       b_in = dev_alloc<float>(mc);
       pack_as(true);
       if (!get("input_blocks.0.0.weight", static_cast<size_t>(mc) * cfg.in_channels * 9, &t)) return false;
@@ -434,6 +461,7 @@ struct Unet {
       float *b0, *b1;
       if (!fp("input_blocks.0.0.bias", mc, &b0) || !fp("cond_linear.bias", mc, &b1)) return false;
       vec_add_kernel<<<(mc + 255) / 256, 256>>>(b0, b1, b_in, mc);
+      if (!split_weight(&w_in, mc, kpad_in, {{0, kpad_in, kpad_in}})) return false;
     }
     // ---- time embedding (fp32)
     if (!fp("time_embed.0.weight", static_cast<size_t>(emb_ch) * mc, &te_w1) || !fp("time_embed.0.bias", emb_ch, &te_b1) ||
@@ -454,7 +482,7 @@ struct Unet {
           !fp(p + "in_layers.2.bias", r.cout, &r.b1))
         return false;
       if (!get(p + "in_layers.2.weight", static_cast<size_t>(r.cout) * r.cin * 9, &t)) return false;
-      r.w1 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * 9 * r.cin);
+      r.w1 = walloc(static_cast<size_t>(r.cout) * 9 * r.cin);
       if (!r.w1) {
         set_error("cudaMalloc failed");
         return false;
@@ -462,9 +490,10 @@ struct Unet {
       pack_as(true);
       CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cin, 3, 3, r.w1, 9 * r.cin, 0, 0));
       consumed.push_back(p + "in_layers.2.weight");
+      if (!split_weight(&r.w1, r.cout, 9 * r.cin, {{0, 9 * r.cin, r.cin}})) return false;
       const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
       if (!get(p + "out_layers.3.weight", static_cast<size_t>(r.cout) * r.cout * 9, &t)) return false;
-      r.w2 = dev_alloc<bf16>(static_cast<size_t>(r.cout) * k2);
+      r.w2 = walloc(static_cast<size_t>(r.cout) * k2);
       r.b2 = dev_alloc<float>(r.cout);
       if (!r.w2 || !r.b2) {
         set_error("cudaMalloc failed");
@@ -483,6 +512,11 @@ struct Unet {
         if (!fp(p + "skip_connection.bias", r.cout, &bs)) return false;
       }
       vec_add_kernel<<<(r.cout + 255) / 256, 256>>>(bo, bs, r.b2, r.cout);
+      {
+        std::vector<std::array<int, 3>> parts = {{0, 9 * r.cout, r.cout}};
+        if (r.skip) parts.push_back({9 * r.cout, r.cin, r.cin});
+        if (!split_weight(&r.w2, r.cout, k2, parts)) return false;
+      }
       // emb_layers (openaimodel.py:203-209) -> rows of the shared [n_all][emb_ch] matrix
       if (!get(p + "emb_layers.1.weight", static_cast<size_t>(r.cout) * emb_ch, &t)) return false;
       CUDA_OK(cudaMemcpy(wall + static_cast<size_t>(r.emb_off) * emb_ch, t->d, t->numel * sizeof(float),
@@ -510,7 +544,7 @@ struct Unet {
         return false;
       pack_as(true);   // QKV and FF1 read LayerNorm outputs
       // fused QKV [3C][C] (attention.py:168-170, no bias)
-      w.wqkv = dev_alloc<bf16>(static_cast<size_t>(3) * C * C);
+      w.wqkv = walloc(static_cast<size_t>(3) * C * C);
       if (!w.wqkv) {
         set_error("cudaMalloc failed");
         return false;
@@ -521,18 +555,26 @@ struct Unet {
         CUDA_OK(launch_pack_matrix(t->d, C, C, w.wqkv, C, 0, i * C, 0));
         consumed.push_back(tb + names[i]);
       }
+      if (!split_weight(&w.wqkv, 3 * C, C, {{0, C, C}})) return false;
       // GEGLU projection [8C][C] interleaved
       const RawTensor* tbias;
       if (!get(tb + "ff.net.0.proj.weight", static_cast<size_t>(8) * C * C, &t) ||
           !get(tb + "ff.net.0.proj.bias", static_cast<size_t>(8) * C, &tbias))
         return false;
-      w.wff1 = dev_alloc<bf16>(static_cast<size_t>(8) * C * C);
+      w.wff1 = walloc(static_cast<size_t>(8) * C * C);
       w.bff1 = dev_alloc<float>(static_cast<size_t>(8) * C);
       if (!w.wff1 || !w.bff1) {
         set_error("cudaMalloc failed");
         return false;
       }
-      pack_geglu_kernel<<<sm_count() * 8, 256>>>(t->d, tbias->d, 4 * C, C, w.wff1, w.bff1, f16_ok ? 1 : 0);
+      if (precise) {
+        // the reference's row order [x | gate]: GEGLU is a separate exact kernel in this mode (precise.cu)
+        CUDA_OK(launch_pack_matrix(t->d, 8 * C, C, w.wff1, C, 0, 0, 0));
+        CUDA_OK(cudaMemcpy(w.bff1, tbias->d, static_cast<size_t>(8) * C * sizeof(float), cudaMemcpyDeviceToDevice));
+        if (!split_weight(&w.wff1, 8 * C, C, {{0, C, C}})) return false;
+      } else {
+        pack_geglu_kernel<<<sm_count() * 8, 256>>>(t->d, tbias->d, 4 * C, C, w.wff1, w.bff1, f16_ok ? 1 : 0);
+      }
       consumed.push_back(tb + "ff.net.0.proj.weight");
     }
     // ---- down / up convs (inputs: the raw residual stream -> bf16)
@@ -541,7 +583,7 @@ struct Unet {
       for (ConvW& c : (pass == 0 ? down : up)) {
         if (!get(c.prefix + "weight", static_cast<size_t>(c.cout) * c.cin * 9, &t)) return false;
         // up: nearest-2x + conv3x3 is folded into four 2x2-tap phase convs on the low-res grid: [4][Cout][4*Cin]
-        c.w = dev_alloc<bf16>(static_cast<size_t>(c.cout) * (pass == 0 ? 9 : 16) * c.cin);
+        c.w = walloc(static_cast<size_t>(c.cout) * (pass == 0 ? 9 : 16) * c.cin);
         if (!c.w) {
           set_error("cudaMalloc failed");
           return false;
@@ -552,6 +594,11 @@ struct Unet {
         CUDA_OK(launch_pack_conv_weight(t->d, c.cout, c.cin, 3, 3, c.w, 9 * c.cin, 0, 0));
         consumed.push_back(c.prefix + "weight");
         if (!fp(c.prefix + "bias", c.cout, &c.b)) return false;
+        if (pass == 0) {
+          if (!split_weight(&c.w, c.cout, 9 * c.cin, {{0, 9 * c.cin, c.cin}})) return false;
+        } else if (!split_weight(&c.w, 4 * c.cout, 4 * c.cin, {{0, 4 * c.cin, c.cin}})) {  // [phase][cout][4 taps][cin]
+          return false;
+        }
       }
     }
     // ---- out: GN -> SiLU -> conv3x3 mc -> out_channels, N padded to 32 (openaimodel.py:770-774)
@@ -562,16 +609,22 @@ struct Unet {
         return false;
       }
       pack_as(true);
-      w_out = dev_alloc<bf16>(static_cast<size_t>(32) * 9 * mc, true);
+      w_out = walloc(static_cast<size_t>(32) * 9 * mc, true);
       b_out = dev_alloc<float>(32, true);
       if (!get("out.2.weight", static_cast<size_t>(cfg.out_channels) * mc * 9, &t)) return false;
       CUDA_OK(launch_pack_conv_weight(t->d, cfg.out_channels, mc, 3, 3, w_out, 9 * mc, 0, 0));
       consumed.push_back("out.2.weight");
       if (!get("out.2.bias", cfg.out_channels, &t)) return false;
       CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice));
+      if (!split_weight(&w_out, 32, 9 * mc, {{0, 9 * mc, mc}})) return false;
     }
     d_violations = dev_alloc<int>(1, true);
     CUDA_OK(cudaDeviceSynchronize());
+    for (void* ptr : split_sources) {
+      owned.erase(std::remove(owned.begin(), owned.end(), ptr), owned.end());
+      cudaFree(ptr);
+    }
+    split_sources.clear();
     // the big fp32 originals are no longer needed
     for (const std::string& name : consumed) {
       auto it = raw.find(name);
@@ -631,78 +684,115 @@ struct Unet {
     return true;
   }
 
-  bool op_gn(PlanCtx& c, const Buf& x1, const Buf* x2, int hw, const float* g, const float* b, float eps, int silu,
-             const Buf& out, const Buf* raw_out, bool out_f16) {
-    if (c.dry) return true;
-    const float* p1 = c.ptr<float>(x1);
-    const float* p2 = x2 ? c.ptr<float>(*x2) : nullptr;
-    const int C1 = x1.C, C2 = x2 ? x2->C : 0;
-    bf16* po = c.ptr<bf16>(out);
-    bf16* pr = raw_out ? c.ptr<bf16>(*raw_out) : nullptr;
-    float* partial = c.gn_partial;
-    const int n_img = c.n_img;
-    // once compact, x1 holds the generated views only while a skip tensor x2 still holds every view
-    const int x2G = (c.compact && x2 != nullptr) ? c.G : 0, x2V = c.V, x2R = c.R, n_layout = c.B * c.V;
-    const int f16 = (out_f16 && f16_ok) ? 1 : 0;
+  // fp32 workspace tensor [M][C] -> its six-segment bf16 operand dst [M][6C] (activation-side order); precise mode
+  void op_split(PlanCtx& c, const Buf& src, const Buf& dst) {
+    if (c.dry) return;
+    const float* ps = c.ptr<float>(src);
+    bf16* pd = c.ptr<bf16>(dst);
+    const size_t M = src.M;
+    const int C = src.C;
     Op op;
-    op.cls = CLS_GN;
+    op.cls = CLS_OTHER;
     op.launches = 1;
     op.flops = 0;
-    op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
-    op.run = [=](cudaStream_t s) {
-      return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s, x2G, x2V, x2R,
-                              n_layout, f16);
-    };
+    op.bytes = static_cast<double>(M) * C * 16;
+    op.run = [=](cudaStream_t s) { return launch_split6(ps, M, C, C, C, pd, static_cast<size_t>(6) * C, 0, s); };
     c.ops->push_back(op);
+  }
+
+  // out (and raw_out) are operand buffers: [M][kx() * C] 16-bit
+  bool op_gn(PlanCtx& c, const Buf& x1, const Buf* x2, int hw, const float* g, const float* b, float eps, int silu,
+             const Buf& out, const Buf* raw_out, bool out_f16) {
+    const int C1 = x1.C, C2 = x2 ? x2->C : 0;
+    Buf t32, r32;  // precise mode: the norm writes fp32 (exact SiLU), which is then split
+    if (precise) {
+      t32 = c.alloc(x1.M, C1 + C2, 4);
+      if (raw_out) r32 = c.alloc(x1.M, C1 + C2, 4);
+    }
+    if (!c.dry) {
+      const float* p1 = c.ptr<float>(x1);
+      const float* p2 = x2 ? c.ptr<float>(*x2) : nullptr;
+      bf16* po = precise ? reinterpret_cast<bf16*>(c.ptr<float>(t32)) : c.ptr<bf16>(out);
+      bf16* pr = raw_out ? (precise ? reinterpret_cast<bf16*>(c.ptr<float>(r32)) : c.ptr<bf16>(*raw_out)) : nullptr;
+      float* partial = c.gn_partial;
+      const int n_img = c.n_img;
+      // once compact, x1 holds the generated views only while a skip tensor x2 still holds every view
+      const int x2G = (c.compact && x2 != nullptr) ? c.G : 0, x2V = c.V, x2R = c.R, n_layout = c.B * c.V;
+      const int fmt = precise ? 2 : ((out_f16 && f16_ok) ? 1 : 0);
+      Op op;
+      op.cls = CLS_GN;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(x1.M) * (C1 + C2) * (4 + 2 + (raw_out ? 2 : 0));
+      op.run = [=](cudaStream_t s) {
+        return launch_groupnorm(p1, C1, p2, C2, n_img, hw, g, b, eps, silu, po, pr, partial, s, x2G, x2V, x2R,
+                                n_layout, fmt);
+      };
+      c.ops->push_back(op);
+    }
+    if (precise) {
+      op_split(c, t32, out);
+      if (raw_out) op_split(c, r32, *raw_out);
+      c.release(t32);
+      c.release(r32);
+    }
     return true;
   }
 
-  bool op_ln(PlanCtx& c, const Buf& x, const float* g, const float* b, const Buf& out) {  // output: fp16 (f16_ok)
-    if (c.dry) return true;
-    const float* px = c.ptr<float>(x);
-    bf16* po = c.ptr<bf16>(out);
-    const int M = x.M, C = x.C;
-    Op op;
-    op.cls = CLS_LN;
-    op.launches = 1;
-    op.flops = 0;
-    op.bytes = static_cast<double>(M) * C * 6;
-    const int f16 = f16_ok ? 1 : 0;
-    op.run = [=](cudaStream_t s) { return launch_layernorm(px, M, C, g, b, 1e-5f, po, s, f16); };
-    c.ops->push_back(op);
+  // out: operand buffer [M][kx() * C]
+  bool op_ln(PlanCtx& c, const Buf& x, const float* g, const float* b, const Buf& out) {
+    Buf t32;
+    if (precise) t32 = c.alloc(x.M, x.C, 4);
+    if (!c.dry) {
+      const float* px = c.ptr<float>(x);
+      bf16* po = precise ? reinterpret_cast<bf16*>(c.ptr<float>(t32)) : c.ptr<bf16>(out);
+      const int M = x.M, C = x.C;
+      const int fmt = precise ? 2 : (f16_ok ? 1 : 0);
+      Op op;
+      op.cls = CLS_LN;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(M) * C * 6;
+      op.run = [=](cudaStream_t s) { return launch_layernorm(px, M, C, g, b, 1e-5f, po, s, fmt); };
+      c.ops->push_back(op);
+    }
+    if (precise) {
+      op_split(c, t32, out);
+      c.release(t32);
+    }
     return true;
   }
 
   // ResBlock._forward (openaimodel.py:256-276); x2 != null: input is cat([x1, x2], channels)
   bool plan_res(PlanCtx& c, const ResW& r, const Buf& x1, const Buf* x2, int H, int W, Buf* out) {
-    const int M = x1.M, hw = H * W;
+    const int M = x1.M, hw = H * W, k = kx();
     const int cin = x1.C + (x2 ? x2->C : 0);
     if (cin != r.cin) {
       set_error("plan: channel mismatch at " + r.prefix);
       return false;
     }
-    Buf a1 = c.alloc(M, cin, 2), xb;
-    if (r.skip) xb = c.alloc(M, cin, 2);
+    Buf a1 = c.alloc(M, k * cin, 2), xb;
+    if (r.skip) xb = c.alloc(M, k * cin, 2);
     if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr, true)) return false;
     Buf h = c.alloc(M, r.cout, 4);
     ConvGeom g{c.n_img, H, W, 9, 1};
     if (!c.dry) {
       GemmPlan p;
-      if (!make_conv_plan(&p, c.ptr<bf16>(a1), g, cin, nullptr, 0, r.w1, r.cout, OUT_F32, c.ptr<float>(h), r.cout,
+      if (!make_conv_plan(&p, c.ptr<bf16>(a1), g, k * cin, nullptr, 0, r.w1, r.cout, OUT_F32, c.ptr<float>(h), r.cout,
                           r.b1, c.emb_all + r.emb_off, hw, n_all, nullptr, 0))
         return false;
       add_gemm_op(c, CLS_CONV, p, true);
     }
     c.release(a1);
-    Buf a2 = c.alloc(M, r.cout, 2);
+    Buf a2 = c.alloc(M, k * r.cout, 2);
     if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr, !r.skip)) return false;
     c.release(h);
     *out = c.alloc(M, r.cout, 4);
     if (!c.dry) {
       GemmPlan p;
       const float* residual = r.skip ? nullptr : c.ptr<float>(x1);
-      if (!make_conv_plan(&p, c.ptr<bf16>(a2), g, r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? cin : 0, r.w2,
-                          r.cout, OUT_F32, c.ptr<float>(*out), r.cout, r.b2, nullptr, 1, 0, residual, r.cout))
+      if (!make_conv_plan(&p, c.ptr<bf16>(a2), g, k * r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? k * cin : 0,
+                          r.w2, r.cout, OUT_F32, c.ptr<float>(*out), r.cout, r.b2, nullptr, 1, 0, residual, r.cout))
         return false;
       add_gemm_op(c, CLS_CONV, p, !r.skip);
     }
@@ -713,6 +803,7 @@ struct Unet {
 
   // SpatioTemporalTransformer.forward (attention.py:375-387) + BasicTransformerBlock (:311-326)
   bool plan_tf(PlanCtx& c, const TfW& w, const Buf& x, int H, int W, Buf* out) {
+    if (precise) return plan_tf_precise(c, w, x, H, W, out);
     const int M = x.M, C = w.C, hw = H * W;
     Buf a = c.alloc(M, C, 2);
     if (!op_gn(c, x, nullptr, hw, w.gn_g, w.gn_b, 1e-6f, 0, a, nullptr, true)) return false;
@@ -766,26 +857,115 @@ struct Unet {
     return true;
   }
 
+  // The same block in fp32-accuracy mode: every GEMM reads six-segment operands and writes fp32, the attention core
+  // and GEGLU are the exact fp32 kernels of precise.cu.
+  bool plan_tf_precise(PlanCtx& c, const TfW& w, const Buf& x, int H, int W, Buf* out) {
+    const int M = x.M, C = w.C, hw = H * W;
+    // fp32 [M][K] operand tensor `src` x weights [N][6K] -> fp32 `o` [M][N] (+ bias, + residual [M][N])
+    auto gemm6 = [&](const Buf& src6, int K, const bf16* Wt, int N, const Buf& o, const float* bias,
+                     const float* residual) -> bool {
+      if (c.dry) return true;
+      GemmPlan p;
+      if (!make_gemm_plan(&p, c.ptr<bf16>(src6), M, 6 * K, nullptr, 0, Wt, N, OUT_F32, c.ptr<float>(o), N, bias, nullptr,
+                          1, 0, residual, N))
+        return false;
+      return add_gemm_op(c, CLS_LINEAR, p, false);
+    };
+    Buf a = c.alloc(M, 6 * C, 2);
+    if (!op_gn(c, x, nullptr, hw, w.gn_g, w.gn_b, 1e-6f, 0, a, nullptr, true)) return false;
+    Buf t0 = c.alloc(M, C, 4);
+    if (!gemm6(a, C, w.wpi, C, t0, w.bpi, nullptr)) return false;
+    c.release(a);
+    Buf n1 = c.alloc(M, 6 * C, 2);
+    if (!op_ln(c, t0, w.ln1_g, w.ln1_b, n1)) return false;
+    Buf qkv = c.alloc(M, 3 * C, 4);
+    if (!gemm6(n1, C, w.wqkv, 3 * C, qkv, nullptr, nullptr)) return false;
+    c.release(n1);
+    Buf o32 = c.alloc(M, C, 4);
+    if (!c.dry) {
+      const float* pq = c.ptr<float>(qkv);
+      float* po = c.ptr<float>(o32);
+      const int L = w.is3d ? c.V * hw : hw;  // attention.py:233 vs :237
+      Op op;
+      op.cls = CLS_ATTN;
+      op.launches = 1;
+      op.flops = 4.0 * (M / L) * (C / 64) * static_cast<double>(L) * L * 64;
+      op.bytes = 0;
+      op.run = [=](cudaStream_t s) { return launch_attention_f32(pq, po, M, C, L, 0.125f, s); };
+      c.ops->push_back(op);
+    }
+    c.release(qkv);
+    Buf o6 = c.alloc(M, 6 * C, 2);
+    op_split(c, o32, o6);
+    c.release(o32);
+    Buf t1 = c.alloc(M, C, 4);
+    if (!gemm6(o6, C, w.wo, C, t1, w.bo, c.dry ? nullptr : c.ptr<float>(t0))) return false;
+    c.release(o6);
+    c.release(t0);
+    Buf n3 = c.alloc(M, 6 * C, 2);
+    if (!op_ln(c, t1, w.ln3_g, w.ln3_b, n3)) return false;
+    Buf u = c.alloc(M, 8 * C, 4);  // [x | gate], the reference's row order
+    if (!gemm6(n3, C, w.wff1, 8 * C, u, w.bff1, nullptr)) return false;
+    c.release(n3);
+    Buf gl = c.alloc(M, 4 * C, 4);
+    if (!c.dry) {
+      const float* pu = c.ptr<float>(u);
+      float* pg = c.ptr<float>(gl);
+      const size_t rows = M;
+      const int inner = 4 * C;
+      Op op;
+      op.cls = CLS_OTHER;
+      op.launches = 1;
+      op.flops = 0;
+      op.bytes = static_cast<double>(M) * C * 48;
+      op.run = [=](cudaStream_t s) { return launch_geglu_f32(pu, rows, inner, pg, s); };
+      c.ops->push_back(op);
+    }
+    c.release(u);
+    Buf g6 = c.alloc(M, 24 * C, 2);
+    op_split(c, gl, g6);
+    c.release(gl);
+    Buf t2 = c.alloc(M, C, 4);
+    if (!gemm6(g6, 4 * C, w.wff2, C, t2, w.bff2, c.dry ? nullptr : c.ptr<float>(t1))) return false;
+    c.release(g6);
+    c.release(t1);
+    Buf t6 = c.alloc(M, 6 * C, 2);
+    op_split(c, t2, t6);
+    c.release(t2);
+    *out = c.alloc(M, C, 4);
+    if (!gemm6(t6, C, w.wpo, C, *out, w.bpo, c.dry ? nullptr : c.ptr<float>(x))) return false;
+    c.release(t6);
+    return true;
+  }
+
   // Downsample (openaimodel.py:135-161): conv3x3 stride 2
   bool plan_down(PlanCtx& c, const ConvW& w, const Buf& x, int H, int W, Buf* out) {
-    const int C = w.cin;
-    Buf pp = c.alloc(x.M, C, 2);
+    const int C = w.cin, k = kx();
+    Buf pp = c.alloc(x.M, k * C, 2), p32;
+    if (precise) p32 = c.alloc(x.M, C, 4);  // fp32 parity planes, then split per pixel
     *out = c.alloc(x.M / 4, w.cout, 4);
     if (!c.dry) {
       const float* px = c.ptr<float>(x);
       bf16* ppp = c.ptr<bf16>(pp);
-      const int n_img = c.n_img;
+      bf16* dst = precise ? reinterpret_cast<bf16*>(c.ptr<float>(p32)) : ppp;
+      const int n_img = c.n_img, to_f32 = precise ? 1 : 0;
       Op op;
       op.cls = CLS_OTHER;
       op.launches = 1;
       op.flops = 0;
       op.bytes = static_cast<double>(x.M) * C * 6;
-      op.run = [=](cudaStream_t s) { return launch_parity_split_bf16(px, n_img, H, W, C, ppp, s); };
+      op.run = [=](cudaStream_t s) { return launch_parity_split_bf16(px, n_img, H, W, C, dst, s, to_f32); };
       c.ops->push_back(op);
+    }
+    if (precise) {
+      op_split(c, p32, pp);
+      c.release(p32);
+    }
+    if (!c.dry) {
       GemmPlan p;
       ConvGeom g{c.n_img, H / 2, W / 2, 9, 2};
-      if (!make_conv_plan(&p, ppp, g, C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1,
-                          0, nullptr, 0))
+      if (!make_conv_plan(&p, c.ptr<bf16>(pp), g, k * C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b,
+                          nullptr, 1, 0, nullptr, 0))
         return false;
       add_gemm_op(c, CLS_CONV, p, false);
     }
@@ -797,10 +977,12 @@ struct Unet {
   // 2x2 neighbourhood of the low-res input, so each of the four phases is a 4-tap conv with pre-summed
   // weights (4/9 of the FLOPs, and the 4x upsampled tensor is never written).
   bool plan_up(PlanCtx& c, const ConvW& w, const Buf& x, int H, int W, Buf* out) {
-    const int C = w.cin;
-    Buf xb = c.alloc(x.M, C, 2);
+    const int C = w.cin, k = kx();
+    Buf xb = c.alloc(x.M, k * C, 2);
     *out = c.alloc(x.M * 4, w.cout, 4);
-    if (!c.dry) {
+    if (precise) {
+      op_split(c, x, xb);
+    } else if (!c.dry) {
       const float* px = c.ptr<float>(x);
       bf16* pb = c.ptr<bf16>(xb);
       const size_t n = static_cast<size_t>(x.M) * C;
@@ -811,15 +993,17 @@ struct Unet {
       op.bytes = static_cast<double>(n) * 6;
       op.run = [=](cudaStream_t s) { return launch_cast_bf16(px, n, pb, s); };
       c.ops->push_back(op);
+    }
+    if (!c.dry) {
       for (int phase = 0; phase < 4; ++phase) {
         GemmPlan p;
         ConvGeom g{c.n_img, H, W, 4, 1};
         g.up_phase = phase;
-        if (!make_conv_plan(&p, pb, g, C, nullptr, 0, w.w + static_cast<size_t>(phase) * w.cout * 4 * C, w.cout, OUT_F32,
-                            c.ptr<float>(*out), w.cout, w.b, nullptr, 1, 0, nullptr, 0))
+        if (!make_conv_plan(&p, c.ptr<bf16>(xb), g, k * C, nullptr, 0, w.w + static_cast<size_t>(phase) * w.cout * 4 * k * C,
+                            w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b, nullptr, 1, 0, nullptr, 0))
           return false;
         const double executed = p.flops;                            // 4 taps on the low-resolution grid
-        p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C;  // algorithmic: the un-folded conv's share
+        p.flops = 2.0 * x.M * static_cast<double>(w.cout) * 9 * C * k;  // algorithmic: the un-folded conv's share
         add_gemm_op(c, CLS_CONV, p, false, executed);
       }
     }
@@ -978,12 +1162,13 @@ struct Unet {
     }
     const int M0 = n_img * H * W;
     // ---- input stage
-    Buf a0 = c.alloc(M0, kpad_in, 2);
+    Buf a0 = c.alloc(M0, kx() * kpad_in, 2), a32;
+    if (precise) a32 = c.alloc(M0, kpad_in, 4);
     Buf h = c.alloc(M0, mc, 4);
     if (!c.dry) {
       IoPtrs* iop = &io;
-      bf16* pa0 = c.ptr<bf16>(a0);
-      const int cin = cfg.in_channels, cc = cfg.condition_channels, kp = kpad_in, in_f16 = f16_ok ? 1 : 0;
+      bf16* pa0 = precise ? reinterpret_cast<bf16*>(c.ptr<float>(a32)) : c.ptr<bf16>(a0);
+      const int cin = cfg.in_channels, cc = cfg.condition_channels, kp = kpad_in, in_f16 = precise ? 2 : (f16_ok ? 1 : 0);
       {
         Op op;
         op.cls = CLS_OTHER;
@@ -1022,9 +1207,15 @@ struct Unet {
           c.ops->push_back(og);
         }
       }
+    }
+    if (precise) {
+      op_split(c, a32, a0);
+      c.release(a32);
+    }
+    if (!c.dry) {
       GemmPlan p;
-      if (!make_gemm_plan(&p, pa0, M0, kp, nullptr, 0, w_in, mc, OUT_F32, c.ptr<float>(h), mc, b_in, nullptr, 1, 0,
-                          nullptr, 0))
+      if (!make_gemm_plan(&p, c.ptr<bf16>(a0), M0, kx() * kpad_in, nullptr, 0, w_in, mc, OUT_F32, c.ptr<float>(h), mc, b_in,
+                          nullptr, 1, 0, nullptr, 0))
         return false;
       add_gemm_op(c, CLS_LINEAR, p, true);
     }
@@ -1068,14 +1259,14 @@ struct Unet {
     }
     // ---- out (on the generated views only once compact)
     const int Mo = c.n_img * H * W;
-    Buf a = c.alloc(Mo, mc, 2);
+    Buf a = c.alloc(Mo, kx() * mc, 2);
     if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr, true)) return false;
     c.release(cur);
     Buf o32 = c.alloc(Mo, 32, 4);
     if (!c.dry) {
       GemmPlan p;
       ConvGeom g{c.n_img, H, W, 9, 1};
-      if (!make_conv_plan(&p, c.ptr<bf16>(a), g, mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
+      if (!make_conv_plan(&p, c.ptr<bf16>(a), g, kx() * mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
                           nullptr, 1, 0, nullptr, 0))
         return false;
       add_gemm_op(c, CLS_CONV, p, true);
@@ -1382,6 +1573,20 @@ int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views) {
   return 0;
 }
 
+int cap4d_b200_unet_set_precision(void* handle, int fp32_accuracy) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  if (u->finalized) {
+    set_error("set_precision must be called before finalize: it decides how the weights are packed");
+    return 1;
+  }
+  u->precise = fp32_accuracy != 0;
+  return 0;
+}
+
 int cap4d_b200_unet_enable_taps(void* handle, int on) {
   Unet* u = static_cast<Unet*>(handle);
   if (u == nullptr) {
@@ -1468,6 +1673,15 @@ int cap4d_b200_unet_collect_timings(void* handle, float* class_ms, int* n_runs) 
     return 1;
   }
   return u->collect_timings(class_ms, n_runs) ? 0 : 6;
+}
+
+int cap4d_b200_unet_plan(void* handle, int B, int V, int H, int W, void* workspace, size_t workspace_bytes) {
+  Unet* u = static_cast<Unet*>(handle);
+  if (u == nullptr) {
+    set_error("null handle");
+    return 1;
+  }
+  return u->ensure_plan(B, V, H, W, workspace, workspace_bytes) ? 0 : 6;
 }
 
 int cap4d_b200_unet_num_launches(void* handle, int* n) {

@@ -90,6 +90,8 @@ class _CudaBackend:
 
     @staticmethod
     def _all_zero(t: torch.Tensor) -> bool:
+        if t.device.type == "cpu" and t.is_contiguous() and t.dtype == torch.float32 and t.numel() % 2 == 0:
+            return not t.numpy().reshape(-1).view(np.uint64).any()  # one pass over the bytes (-0.0 counts as data)
         return not bool(torch.count_nonzero(t))
 
     def begin(self, st, ref_cond, ref_uncond, gen_cond, gen_uncond, all_x) -> None:

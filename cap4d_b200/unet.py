@@ -63,8 +63,11 @@ class B200MMDMUnet(torch.nn.Module):
     """Drop-in for MMDMUnetModel on one B200.  Weights are uploaded and repacked once."""
 
     def __init__(self, config: Mapping, state_dict: Mapping[str, torch.Tensor], device: Optional[torch.device] = None,
-                 keep_state: bool = False, lazy: bool = False):
-        """keep_state: keep references (no copies) to the fp32 `state_dict` tensors, which is what lets the module
+                 keep_state: bool = False, lazy: bool = False, precision: str = "bf16"):
+        """precision: "bf16" (default: 16-bit tensor-core operands, fp32 accumulation, <= 1e-2 of the fp32 reference)
+        or "fp32" (the reference's own accuracy, <= 1e-4: exact bf16 x 3 operand splits on the same tensor-core
+        kernels, exact pointwise maths; an order of magnitude slower).
+        keep_state: keep references (no copies) to the fp32 `state_dict` tensors, which is what lets the module
         be deep-copied and moved to another GPU like the reference's nn.Module (generate_images.py:62-71:
         `copy.deepcopy(model).to(f"cuda:{i}")`).  lazy: upload / repack the weights at the first forward or
         `.to(device)` instead of now (implies keep_state)."""
@@ -82,6 +85,9 @@ class B200MMDMUnet(torch.nn.Module):
         self._ws: Dict = {}  # (B, V, H, W, R) -> workspace tensor (a launch plan is bound to its workspace)
         self.dtype = torch.float32
         self.time_steps = int(config["time_steps"])
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         _make_config(config)  # validate now, even when lazy
         self._state = dict(state_dict) if (keep_state or lazy) else None
         if not lazy:
@@ -95,6 +101,7 @@ class B200MMDMUnet(torch.nn.Module):
         with torch.cuda.device(self._device):
             _lib.check(self._lib.cap4d_b200_unet_create(ctypes.byref(cfg), ctypes.byref(handle)), "unet_create")
             try:
+                _lib.check(self._lib.cap4d_b200_unet_set_precision(handle, int(self.precision == "fp32")), "set_precision")
                 for name, t in state_dict.items():
                     t32 = t.detach().to(dtype=torch.float32).contiguous()
                     shape = (ctypes.c_int64 * max(1, t32.dim()))(*t32.shape)
@@ -172,11 +179,11 @@ class B200MMDMUnet(torch.nn.Module):
         return cls(config, sd, device=dev)
 
     @classmethod
-    def from_reference(cls, ref_unet, device=None, lazy: bool = False) -> "B200MMDMUnet":
+    def from_reference(cls, ref_unet, device=None, lazy: bool = False, precision: str = "bf16") -> "B200MMDMUnet":
         """Built from a constructed reference MMDMUnetModel; keeps references to its fp32 tensors so that the
         result can be deep-copied / moved between GPUs like the module it replaces."""
         sd = {k: v.detach() for k, v in ref_unet.state_dict().items()}
-        return cls(config_from_reference(ref_unet), sd, device=device, keep_state=True, lazy=lazy)
+        return cls(config_from_reference(ref_unet), sd, device=device, keep_state=True, lazy=lazy, precision=precision)
 
     # The reference copies and moves whole models (generate_images.py:62-71: copy.deepcopy(model).to("cuda:i")).
     # The device state of this module lives behind the library handle, so a copy shares the fp32 source tensors
@@ -194,6 +201,7 @@ class B200MMDMUnet(torch.nn.Module):
         new._ws = {}
         new.dtype = self.dtype
         new.time_steps = self.time_steps
+        new.precision = self.precision
         new._state = self._state
         new.record_every = self.record_every
         memo[id(self)] = new
@@ -394,6 +402,12 @@ class B200MMDMUnet(torch.nn.Module):
             )
         return out, {n: float(ms[i]) for i, n in enumerate(_lib.CLASS_NAMES)}
 
+    def select_plan(self, B: int, V: int, H: int, W: int, n_ref_views: int = 0) -> None:
+        """Make the launch plan of this batch shape the current one (what class_stats / num_launches describe)."""
+        with torch.cuda.device(self._device):
+            ws = self._workspace(B, V, H, W, int(n_ref_views))
+            _lib.check(self._lib.cap4d_b200_unet_plan(self._handle, B, V, H, W, ws.data_ptr(), ws.numel()), "unet_plan")
+
     def class_stats(self):
         """Algorithmic FLOPs / bytes / launches per kernel class of the current plan."""
         self._ensure_built()
@@ -413,13 +427,13 @@ class B200MMDMUnet(torch.nn.Module):
         return n.value
 
 
-def install(mmldm, device=None, lazy: bool = False) -> B200MMDMUnet:
+def install(mmldm, device=None, lazy: bool = False, precision: str = "bf16") -> B200MMDMUnet:
     """Replace `mmldm.model.diffusion_model` (ddpm.py:1318) by the B200 implementation, in place.
 
     lazy=True is the form for the reference's own driver (generate_images.py:59-71): call it right after
     `load_model(...)` while the model is still on the CPU; every `copy.deepcopy(model).to(f"cuda:{i}")` that
     follows then uploads and repacks the weights once, on its own GPU."""
     ref_unet = mmldm.model.diffusion_model
-    new = B200MMDMUnet.from_reference(ref_unet, device=device, lazy=lazy)
+    new = B200MMDMUnet.from_reference(ref_unet, device=device, lazy=lazy, precision=precision)
     mmldm.model.diffusion_model = new
     return new

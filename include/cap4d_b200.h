@@ -59,6 +59,15 @@ int cap4d_b200_unet_load_weight(void* handle, const char* name, const float* dat
 int cap4d_b200_unet_num_params(void* handle, int* n);
 int cap4d_b200_unet_param_info(void* handle, int index, char* name, int name_capacity, int64_t* shape, int* ndim);
 
+/* Arithmetic of this handle; call between create and finalize.
+ *   0 (default)  16-bit tensor-core operands, fp32 accumulation: noise prediction within 1e-2 of the fp32 reference
+ *                (measured 5.1e-3 .. 6.7e-3 on the production architecture)
+ *   1            fp32 accuracy (the reference's own precision, openaimodel.py:522): every operand is the exact
+ *                three-way bf16 split of the fp32 tensor and products keep all terms >= 2^-16 (six bf16 MMAs per
+ *                product on the same tcgen05 kernels), exact SiLU / GELU / softmax, fp32 attention; within 1e-4 of
+ *                the reference, an order of magnitude slower. */
+int cap4d_b200_unet_set_precision(void* handle, int fp32_accuracy);
+
 /* Repack all weights for the tensor-core kernels (bf16, K-major, fused QKV / GEGLU / skip-conv
  * layouts).  Fails if any parameter of the topology was not loaded. */
 int cap4d_b200_unet_finalize(void* handle);
@@ -95,6 +104,9 @@ int cap4d_b200_unet_forward(void* handle, const float* x, const int64_t* timeste
  * classes: 0 conv3x3 (tcgen05 implicit GEMM), 1 linear (tcgen05 GEMM), 2 attention core,
  *          3 GroupNorm, 4 LayerNorm, 5 other (pack / mix / resample / embedding). */
 #define CAP4D_B200_N_CLASSES 6
+/* Build (or fetch from the cache) the launch plan of a batch shape without running it and make it the current plan,
+ * which is what num_launches / class_stats / class_exec_flops describe. */
+int cap4d_b200_unet_plan(void* handle, int B, int V, int H, int W, void* workspace, size_t workspace_bytes);
 int cap4d_b200_unet_num_launches(void* handle, int* n);
 int cap4d_b200_unet_class_stats(void* handle, double* flops, double* bytes, int* launches);
 /* class_stats reports ALGORITHMIC FLOPs (the reference op's count); this returns what the tensor core executes per

@@ -272,7 +272,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, max_period: int = 10000) -> to
 
 def _gn(x, sd, p, eps):
     # GroupNorm32: fp32 group norm with 32 groups (util.py:217-219, :202-208)
-    return F.group_norm(x.float(), 32, sd[p + "weight"], sd[p + "bias"], eps)
+    return F.group_norm(_c(x), 32, sd[p + "weight"], sd[p + "bias"], eps)
 
 
 def res_block(sd, p, x, emb):
@@ -284,6 +284,16 @@ def res_block(sd, p, x, emb):
     if (p + "skip_connection.weight") in sd:
         x = F.conv2d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
     return x + h
+
+
+# Arithmetic type of unet_forward's internal casts (the reference's `.float()` / `.type(self.dtype)` calls).  float32 is
+# the reference; float64 - with a float64 state_dict and inputs - gives the ground truth that tells the rounding noise of
+# two correct fp32 implementations apart from a real error (tests/test_gpu_fp32_mode.py).
+COMPUTE_DTYPE = torch.float32
+
+
+def _c(x: torch.Tensor) -> torch.Tensor:
+    return x.to(COMPUTE_DTYPE)
 
 
 # "legacy": the reference's materialised softmax (what the parity tests check against).  "sdpa": the same contraction
@@ -312,7 +322,7 @@ def attention_core(q, k, v, heads: int, views: int, is3d: bool):
     if ATTENTION_IMPL == "sdpa":
         out = F.scaled_dot_product_attention(q[None], k[None], v[None], scale=d ** -0.5)[0]
     else:
-        sim = torch.einsum("bid,bjd->bij", q.float(), k.float()) * (d ** -0.5)
+        sim = torch.einsum("bid,bjd->bij", _c(q), _c(k)) * (d ** -0.5)
         sim = sim.softmax(dim=-1)
         out = torch.einsum("bij,bjd->bid", sim, v)
     if is3d:
@@ -376,14 +386,14 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, timest
     B, V = x.shape[:2]
     h = x.reshape(B * V, *x.shape[2:])
     t = timesteps.reshape(B * V)
-    pos = control["pos_enc"].reshape(B * V, *control["pos_enc"].shape[2:]).float()
+    pos = _c(control["pos_enc"].reshape(B * V, *control["pos_enc"].shape[2:]))
     pos_emb = F.linear(pos, sd["cond_linear.weight"], sd["cond_linear.bias"]).permute(0, 3, 1, 2)
-    temb = timestep_embedding(t, cfg["model_channels"])
+    temb = _c(timestep_embedding(t, cfg["model_channels"]))
     emb = F.linear(F.silu(F.linear(temb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])),
                    sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     ib, mid, ob = unet_topology(cfg)
     hs = []
-    h = h.float()
+    h = _c(h)
     for i, blk in enumerate(ib):
         h = _run_block(sd, blk, h, emb, V)
         if i == 0:
