@@ -42,7 +42,12 @@ int env_int(const char* name, int dflt) {
 // `waves` items per resident block); large images get more chunks so that the images in flight stay L2-sized.
 // Measured (scripts/gn_sweep.sh, round 2): small chunks that would make the second pass a guaranteed L2 hit cost
 // more in per-item overhead than the DRAM re-read they save, with 256-thread blocks and with one 1024-thread
-// block per SM alike - the defaults are the best of the sweep at 16 and 80 images.
+// block per SM alike - the defaults are the best of the sweep at 16 and 80 images.  The same holds for keeping the
+// chunk in REGISTERS between the phases (one HBM read, 40 KB items, two in flight per block): correct, 22.9 GB of
+// DRAM traffic per call instead of 33.5, and 1.45-2.5x SLOWER (264 / 739 / 1265 us against 182 / 342 / 506 us on the
+// three level-0 shapes) - an item then lasts ~2 us of transfer against ~5-9 us of per-item round trips (ticket,
+// partials + fence, arrive, flag poll, done counter).  The fix for the re-read is statistics from the producer's
+// epilogue, not a different GroupNorm kernel.
 __host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img, int resident) {
   static const int l2_mb = env_int("CAP4D_GN_L2_MB", 160), waves = env_int("CAP4D_GN_WAVES", 2);
   GnGeom g;
