@@ -77,6 +77,8 @@ __host__ GnGeom gn_geometry(int C1, int C2, int hw, int n_img, int resident) {
   if (resident < 1) resident = 1;
   const double image_mb = static_cast<double>(hw) * g.C * 4 / (1024.0 * 1024.0);
   int chunks = static_cast<int>(resident * image_mb / l2_mb) + 1;            // (1) L2 residency
+  if (2.0 * image_mb > l2_mb) chunks = 1;  // an image that cannot share L2 with a second one (VAE decoder, 512^2 x 128:
+                                           // 134 MB) is re-read from HBM whatever the chunking: fewest, largest chunks
   const int fill = (waves * resident + n_img - 1) / n_img;                   // (2) enough items
   if (chunks < fill) chunks = fill;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;

@@ -46,7 +46,7 @@ out = {"what": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__ti
                "(scripts/ncu_bench_traffic.sh): launches of the first U-Net calls of the timed region, cold-cache and "
                "serialised (compare shares, not absolutes)",
        "source_digest": B._digest(), "groups_per_call": gpc, "workload": workload, "n_launches": sum(len(s) for s in launch_ids.values()),
-       "library_kernels": sorted(k for k in kernels if k.startswith("at") or "at::" in k or "elementwise_kernel" in k or "vectorized" in k),
+       "library_kernels": sorted(k for k in kernels if k.startswith("at::") or "at::native" in k or "elementwise_kernel" in k or "vectorized_" in k or "cutlass" in k or "cudnn" in k),
        "kernels": kernels}
 with open(dst, "w") as fh:
     json.dump(out, fh, indent=1)
