@@ -130,7 +130,7 @@ struct Unet {
   int ref_views = 0;
   int* d_violations = nullptr;  // broken n_ref_views promises seen by the output mix (device counter)
   // Debug taps (cap4d_b200_unet_enable_taps): the fp32 NHWC activation after every block of the topology is copied
-  // into a slot of the workspace, for per-block error budgets against the oracle (tests/test_gpu_parity_budget.py).
+  // into a slot of the workspace, for per-block error budgets against the fp32 reference arithmetic (tests/test_gpu_parity_budget.py).
   bool taps_on = false;
   struct TapInfo {
     std::string name;
