@@ -91,8 +91,9 @@ class _CudaBackend:
     @staticmethod
     def _all_zero(t: torch.Tensor) -> bool:
         if t.device.type == "cpu" and t.is_contiguous() and t.dtype == torch.float32 and t.numel() % 2 == 0:
-            return not t.numpy().reshape(-1).view(np.uint64).any()  # one pass over the bytes (-0.0 counts as data)
-        return not bool(torch.count_nonzero(t))
+            if not t.numpy().reshape(-1).view(np.uint64).any():  # one pass over the bytes: all +0.0
+                return True
+        return not bool(torch.count_nonzero(t))  # -0.0 (the reference's `z_input * 0.`) is zero too
 
     def begin(self, st, ref_cond, ref_uncond, gen_cond, gen_uncond, all_x) -> None:
         dev = self.device
