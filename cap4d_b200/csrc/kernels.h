@@ -190,6 +190,10 @@ cudaError_t launch_cast_bf16(const float* x, size_t n, bf16* out, cudaStream_t s
 // group_width-wide segments, [l|h|m|m|h|h] (worder 0: activation side) or [h|l|m|h|m|h] (worder 1: weight side)
 cudaError_t launch_split6(const float* x, size_t rows, int cols, size_t ldx, int group_width, bf16* out, size_t ld_out,
                           int worder, cudaStream_t stream);
+// conv operands: the five small-term segments per group go to out5 [rows][ld5] ([l|h|m|m|h] / weights [h|l|m|h|m]),
+// the leading segment (h) to out1 [rows][ld1]
+cudaError_t launch_split51(const float* x, size_t rows, int cols, size_t ldx, int group_width, bf16* out5, size_t ld5,
+                           bf16* out1, size_t ld1, int worder, cudaStream_t stream);
 // out[r][c] = u[r][c] * gelu(u[r][inner + c]) (erf form, exact), u fp32 [rows][2 inner]
 cudaError_t launch_geglu_f32(const float* u, size_t rows, int inner, float* out, cudaStream_t stream);
 // in-place softmax(scale * s) over the rows of fp32 [rows][L]

@@ -67,6 +67,40 @@ __global__ void split6_kernel(const float* __restrict__ x, size_t rows, int cols
   }
 }
 
+// The same split for the operands of a 3x3 CONVOLUTION, whose K runs tap-major: with all six segments in one
+// accumulation the leading ah * wh products of the first taps fill the accumulator before the small terms of the later
+// taps arrive, and the tensor core's truncating fp32 accumulation then costs 6 K / 16 roundings at full magnitude.
+// The five small terms and the leading term therefore go to two tensors - out5 [rows][5 cols] ([l|h|m|m|h] per group;
+// weights [h|l|m|h|m]) and out1 [rows][cols] (h; weights h) - convolved by two launches whose results meet in the
+// second launch's fp32 residual add (IEEE).
+__global__ void split51_kernel(const float* __restrict__ x, size_t rows, int cols, size_t ldx, int gw,
+                               bf16* __restrict__ out5, size_t ld5, bf16* __restrict__ out1, size_t ld1, int worder) {
+  const size_t total = rows * static_cast<size_t>(cols);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const int g = c / gw, j = c - g * gw;
+    bf16 h, m, l;
+    split3(x[r * ldx + c], h, m, l);
+    bf16* o = out5 + r * ld5 + static_cast<size_t>(g) * 5 * gw + j;
+    if (worder) {  // [h | l | m | h | m]
+      o[0] = h;
+      o[gw] = l;
+      o[2 * gw] = m;
+      o[3 * gw] = h;
+      o[4 * gw] = m;
+    } else {       // [l | h | m | m | h]
+      o[0] = l;
+      o[gw] = h;
+      o[2 * gw] = m;
+      o[3 * gw] = m;
+      o[4 * gw] = h;
+    }
+    out1[r * ld1 + c] = h;
+  }
+}
+
 // GEGLU (attention.py:68-75), exact: u = [x | gate] fp32 [rows][2 inner] -> out[r][c] = x * gelu(gate), erf form
 __global__ void geglu_f32_kernel(const float* __restrict__ u, size_t rows, int inner, float* __restrict__ out) {
   const size_t total = rows * static_cast<size_t>(inner);
@@ -228,6 +262,17 @@ cudaError_t launch_split6(const float* x, size_t rows, int cols, size_t ldx, int
   }
   if (rows == 0 || cols == 0) return cudaSuccess;
   split6_kernel<<<pgrid(rows * cols, 256), 256, 0, stream>>>(x, rows, cols, ldx, group_width, out, ld_out, worder);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split51(const float* x, size_t rows, int cols, size_t ldx, int group_width, bf16* out5, size_t ld5,
+                           bf16* out1, size_t ld1, int worder, cudaStream_t stream) {
+  if (group_width <= 0 || cols % group_width != 0) {
+    set_error("split51: the column count must be a multiple of the group width");
+    return cudaErrorInvalidValue;
+  }
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  split51_kernel<<<pgrid(rows * cols, 256), 256, 0, stream>>>(x, rows, cols, ldx, group_width, out5, ld5, out1, ld1, worder);
   return cudaGetLastError();
 }
 

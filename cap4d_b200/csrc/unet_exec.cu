@@ -401,7 +401,9 @@ struct Unet {
   std::vector<void*> split_sources;  // fp32 repacked weights, freed once their splits exist
   // precise mode: *w holds fp32 [rows][K] in the GEMM's K order -> bf16 [rows][6 K], weight-side segment order.
   // parts: (first column, column count, segment width) - the K ranges that face different operand tensors
-  bool split_weight(bf16** w, int rows, int K, const std::vector<std::array<int, 3>>& parts) {
+  // conv51: the layout of a 3x3 conv's weights (precise.cu, split51): [rows][5 K] small-term segments followed by
+  // [rows][K] leading segments, for the two launches of conv51()
+  bool split_weight(bf16** w, int rows, int K, const std::vector<std::array<int, 3>>& parts, bool conv51 = false) {
     if (!precise) return true;
     bf16* out = dev_alloc<bf16>(static_cast<size_t>(rows) * 6 * K);
     if (!out) {
@@ -409,9 +411,15 @@ struct Unet {
       return false;
     }
     const float* src = reinterpret_cast<const float*>(*w);
-    for (const auto& pt : parts)
-      CUDA_OK(launch_split6(src + pt[0], rows, pt[1], K, pt[2], out + static_cast<size_t>(6) * pt[0],
-                            static_cast<size_t>(6) * K, 1, 0));
+    bf16* hi = out + static_cast<size_t>(rows) * 5 * K;
+    for (const auto& pt : parts) {
+      if (conv51)
+        CUDA_OK(launch_split51(src + pt[0], rows, pt[1], K, pt[2], out + static_cast<size_t>(5) * pt[0],
+                               static_cast<size_t>(5) * K, hi + pt[0], K, 1, 0));
+      else
+        CUDA_OK(launch_split6(src + pt[0], rows, pt[1], K, pt[2], out + static_cast<size_t>(6) * pt[0],
+                              static_cast<size_t>(6) * K, 1, 0));
+    }
     split_sources.push_back(*w);
     *w = out;
     return true;
@@ -490,7 +498,7 @@ struct Unet {
       pack_as(true);
       CUDA_OK(launch_pack_conv_weight(t->d, r.cout, r.cin, 3, 3, r.w1, 9 * r.cin, 0, 0));
       consumed.push_back(p + "in_layers.2.weight");
-      if (!split_weight(&r.w1, r.cout, 9 * r.cin, {{0, 9 * r.cin, r.cin}})) return false;
+      if (!split_weight(&r.w1, r.cout, 9 * r.cin, {{0, 9 * r.cin, r.cin}}, true)) return false;
       const int k2 = 9 * r.cout + (r.skip ? r.cin : 0);
       if (!get(p + "out_layers.3.weight", static_cast<size_t>(r.cout) * r.cout * 9, &t)) return false;
       r.w2 = walloc(static_cast<size_t>(r.cout) * k2);
@@ -515,7 +523,7 @@ struct Unet {
       {
         std::vector<std::array<int, 3>> parts = {{0, 9 * r.cout, r.cout}};
         if (r.skip) parts.push_back({9 * r.cout, r.cin, r.cin});
-        if (!split_weight(&r.w2, r.cout, k2, parts)) return false;
+        if (!split_weight(&r.w2, r.cout, k2, parts, true)) return false;
       }
       // emb_layers (openaimodel.py:203-209) -> rows of the shared [n_all][emb_ch] matrix
       if (!get(p + "emb_layers.1.weight", static_cast<size_t>(r.cout) * emb_ch, &t)) return false;
@@ -595,7 +603,7 @@ struct Unet {
         consumed.push_back(c.prefix + "weight");
         if (!fp(c.prefix + "bias", c.cout, &c.b)) return false;
         if (pass == 0) {
-          if (!split_weight(&c.w, c.cout, 9 * c.cin, {{0, 9 * c.cin, c.cin}})) return false;
+          if (!split_weight(&c.w, c.cout, 9 * c.cin, {{0, 9 * c.cin, c.cin}}, true)) return false;
         } else if (!split_weight(&c.w, 4 * c.cout, 4 * c.cin, {{0, 4 * c.cin, c.cin}})) {  // [phase][cout][4 taps][cin]
           return false;
         }
@@ -616,7 +624,7 @@ struct Unet {
       consumed.push_back("out.2.weight");
       if (!get("out.2.bias", cfg.out_channels, &t)) return false;
       CUDA_OK(cudaMemcpy(b_out, t->d, cfg.out_channels * sizeof(float), cudaMemcpyDeviceToDevice));
-      if (!split_weight(&w_out, 32, 9 * mc, {{0, 9 * mc, mc}})) return false;
+      if (!split_weight(&w_out, 32, 9 * mc, {{0, 9 * mc, mc}}, true)) return false;
     }
     d_violations = dev_alloc<int>(1, true);
     CUDA_OK(cudaDeviceSynchronize());
@@ -685,7 +693,8 @@ struct Unet {
   }
 
   // fp32 workspace tensor [M][C] -> its six-segment bf16 operand dst [M][6C] (activation-side order); precise mode
-  void op_split(PlanCtx& c, const Buf& src, const Buf& dst) {
+  // conv51: dst is laid out for conv51() - [M][5C] small-term segments followed by [M][C] leading segments
+  void op_split(PlanCtx& c, const Buf& src, const Buf& dst, bool conv51 = false) {
     if (c.dry) return;
     const float* ps = c.ptr<float>(src);
     bf16* pd = c.ptr<bf16>(dst);
@@ -696,13 +705,46 @@ struct Unet {
     op.launches = 1;
     op.flops = 0;
     op.bytes = static_cast<double>(M) * C * 16;
-    op.run = [=](cudaStream_t s) { return launch_split6(ps, M, C, C, C, pd, static_cast<size_t>(6) * C, 0, s); };
+    if (conv51)
+      op.run = [=](cudaStream_t s) {
+        return launch_split51(ps, M, C, C, C, pd, static_cast<size_t>(5) * C, pd + M * 5 * C, C, 0, s);
+      };
+    else
+      op.run = [=](cudaStream_t s) { return launch_split6(ps, M, C, C, C, pd, static_cast<size_t>(6) * C, 0, s); };
     c.ops->push_back(op);
+  }
+
+  // precise mode: a 3x3 conv over conv51-laid-out operands = the small-terms launch (bias, timestep bias, residual)
+  // followed by the leading-term launch, which adds the first result as its fp32 residual.  Cin / K2: channels of ONE
+  // segment of the conv operand `a` / of the appended 1x1 operand `a2`.
+  bool conv51(PlanCtx& c, const ConvGeom& g, const Buf& a, int Cin, const Buf* a2, int K2, const bf16* w, int N,
+              const Buf& out, const float* bias, const float* rowbias, int rb_div, int rb_ld, const float* residual) {
+    Buf tmp = c.alloc(out.M, N, 4);
+    if (!c.dry) {
+      const size_t Ma = a.M;
+      const bf16* a_lo = c.ptr<bf16>(a);
+      const bf16* a_hi = a_lo + Ma * 5 * Cin;
+      const bf16* a2_lo = a2 ? c.ptr<bf16>(*a2) : nullptr;
+      const bf16* a2_hi = a2 ? a2_lo + static_cast<size_t>(a2->M) * 5 * K2 : nullptr;
+      const int Kt = 9 * Cin + (a2 ? K2 : 0);
+      const bf16* w_hi = w + static_cast<size_t>(N) * 5 * Kt;
+      GemmPlan p;
+      if (!make_conv_plan(&p, a_lo, g, 5 * Cin, a2_lo, a2 ? 5 * K2 : 0, w, N, OUT_F32, c.ptr<float>(tmp), N, bias, rowbias,
+                          rb_div, rb_ld, residual, N))
+        return false;
+      add_gemm_op(c, CLS_CONV, p, false);
+      if (!make_conv_plan(&p, a_hi, g, Cin, a2_hi, a2 ? K2 : 0, w_hi, N, OUT_F32, c.ptr<float>(out), N, nullptr, nullptr, 1,
+                          0, c.ptr<float>(tmp), N))
+        return false;
+      add_gemm_op(c, CLS_CONV, p, false);
+    }
+    c.release(tmp);
+    return true;
   }
 
   // out (and raw_out) are operand buffers: [M][kx() * C] 16-bit
   bool op_gn(PlanCtx& c, const Buf& x1, const Buf* x2, int hw, const float* g, const float* b, float eps, int silu,
-             const Buf& out, const Buf* raw_out, bool out_f16) {
+             const Buf& out, const Buf* raw_out, bool out_f16, bool conv_operand = false) {
     const int C1 = x1.C, C2 = x2 ? x2->C : 0;
     Buf t32, r32;  // precise mode: the norm writes fp32 (exact SiLU), which is then split
     if (precise) {
@@ -731,8 +773,8 @@ struct Unet {
       c.ops->push_back(op);
     }
     if (precise) {
-      op_split(c, t32, out);
-      if (raw_out) op_split(c, r32, *raw_out);
+      op_split(c, t32, out, conv_operand);
+      if (raw_out) op_split(c, r32, *raw_out, conv_operand);
       c.release(t32);
       c.release(r32);
     }
@@ -773,10 +815,14 @@ struct Unet {
     }
     Buf a1 = c.alloc(M, k * cin, 2), xb;
     if (r.skip) xb = c.alloc(M, k * cin, 2);
-    if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr, true)) return false;
+    if (!op_gn(c, x1, x2, hw, r.gn1_g, r.gn1_b, 1e-5f, 1, a1, r.skip ? &xb : nullptr, true, true)) return false;
     Buf h = c.alloc(M, r.cout, 4);
     ConvGeom g{c.n_img, H, W, 9, 1};
-    if (!c.dry) {
+    if (precise) {
+      if (!conv51(c, g, a1, cin, nullptr, 0, r.w1, r.cout, h, r.b1, c.dry ? nullptr : c.emb_all + r.emb_off, hw, n_all,
+                  nullptr))
+        return false;
+    } else if (!c.dry) {
       GemmPlan p;
       if (!make_conv_plan(&p, c.ptr<bf16>(a1), g, k * cin, nullptr, 0, r.w1, r.cout, OUT_F32, c.ptr<float>(h), r.cout,
                           r.b1, c.emb_all + r.emb_off, hw, n_all, nullptr, 0))
@@ -785,10 +831,14 @@ struct Unet {
     }
     c.release(a1);
     Buf a2 = c.alloc(M, k * r.cout, 2);
-    if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr, !r.skip)) return false;
+    if (!op_gn(c, h, nullptr, hw, r.gn2_g, r.gn2_b, 1e-5f, 1, a2, nullptr, !r.skip, true)) return false;
     c.release(h);
     *out = c.alloc(M, r.cout, 4);
-    if (!c.dry) {
+    if (precise) {
+      if (!conv51(c, g, a2, r.cout, r.skip ? &xb : nullptr, cin, r.w2, r.cout, *out, r.b2, nullptr, 1, 0,
+                  (r.skip || c.dry) ? nullptr : c.ptr<float>(x1)))
+        return false;
+    } else if (!c.dry) {
       GemmPlan p;
       const float* residual = r.skip ? nullptr : c.ptr<float>(x1);
       if (!make_conv_plan(&p, c.ptr<bf16>(a2), g, k * r.cout, r.skip ? c.ptr<bf16>(xb) : nullptr, r.skip ? k * cin : 0,
@@ -958,10 +1008,11 @@ struct Unet {
       c.ops->push_back(op);
     }
     if (precise) {
-      op_split(c, p32, pp);
+      op_split(c, p32, pp, true);
       c.release(p32);
-    }
-    if (!c.dry) {
+      ConvGeom g{c.n_img, H / 2, W / 2, 9, 2};
+      if (!conv51(c, g, pp, C, nullptr, 0, w.w, w.cout, *out, w.b, nullptr, 1, 0, nullptr)) return false;
+    } else if (!c.dry) {
       GemmPlan p;
       ConvGeom g{c.n_img, H / 2, W / 2, 9, 2};
       if (!make_conv_plan(&p, c.ptr<bf16>(pp), g, k * C, nullptr, 0, w.w, w.cout, OUT_F32, c.ptr<float>(*out), w.cout, w.b,
@@ -1260,16 +1311,22 @@ struct Unet {
     // ---- out (on the generated views only once compact)
     const int Mo = c.n_img * H * W;
     Buf a = c.alloc(Mo, kx() * mc, 2);
-    if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr, true)) return false;
+    if (!op_gn(c, cur, nullptr, H * W, out_gn_g, out_gn_b, 1e-5f, 1, a, nullptr, true, true)) return false;
     c.release(cur);
     Buf o32 = c.alloc(Mo, 32, 4);
-    if (!c.dry) {
-      GemmPlan p;
+    if (precise) {
       ConvGeom g{c.n_img, H, W, 9, 1};
-      if (!make_conv_plan(&p, c.ptr<bf16>(a), g, kx() * mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
-                          nullptr, 1, 0, nullptr, 0))
-        return false;
-      add_gemm_op(c, CLS_CONV, p, true);
+      if (!conv51(c, g, a, mc, nullptr, 0, w_out, 32, o32, b_out, nullptr, 1, 0, nullptr)) return false;
+    }
+    if (!c.dry) {
+      if (!precise) {
+        GemmPlan p;
+        ConvGeom g{c.n_img, H, W, 9, 1};
+        if (!make_conv_plan(&p, c.ptr<bf16>(a), g, mc, nullptr, 0, w_out, 32, OUT_F32, c.ptr<float>(o32), 32, b_out,
+                            nullptr, 1, 0, nullptr, 0))
+          return false;
+        add_gemm_op(c, CLS_CONV, p, true);
+      }
       IoPtrs* iop = &io;
       const float* po = c.ptr<float>(o32);
       const int cout = cfg.out_channels;

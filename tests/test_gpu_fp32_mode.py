@@ -70,10 +70,9 @@ def test_fp32_mode_matches_oracle(cuda_device, tiny_fp32, B, V, H, W, R, tstep):
 
 def test_fp32_mode_production_config(cuda_device):
     """cap4d_mmdm_final.yaml (815.5 M parameters), one group's CFG pair at 64x64.  Two checks: within 1e-4 of the
-    fp32 reference arithmetic (the oracle on the GPU, TF32 off) and within 1e-4 of a float64 evaluation of the same
-    network (the truth; the fp32 oracle's own distance from it is printed next to it: the tensor core accumulates
-    its fp32 sums with truncation, which over the 6x longer K of the split operands costs a few 1e-5 that an IEEE
-    fp32 implementation does not pay - DESIGN.md).  Also reports the slow-down."""
+    fp32 reference arithmetic (the oracle on the GPU, TF32 off), and - against a float64 evaluation of the same network,
+    the truth - about as close as that IEEE-fp32 evaluation itself is (measured 1.7e-5 against 1.2e-5).  Also reports
+    the slow-down."""
     from cap4d_b200 import B200MMDMUnet
 
     cfg = O.PRODUCTION_CONFIG
@@ -107,4 +106,4 @@ def test_fp32_mode_production_config(cuda_device):
           f"fp32 oracle {ref_truth:.3e}; forward {sum(ms.values()):.1f} ms ({ms})")
     assert torch.equal(y[:, :1], ref[:, :1])
     assert err < FP32_TOL
-    assert err_truth < FP32_TOL
+    assert err_truth < FP32_TOL and err_truth < 2.0 * ref_truth + 1e-5
