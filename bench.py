@@ -432,8 +432,15 @@ def main():
     st2 = s2.begin(S_TOTAL, rc, ru, gc, gu, LATENT, V=V, R_max=4, cfg_scale=CFG_SCALE)   # H2D of everything
     torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
+    probe = torch.empty(1024, dtype=torch.float32).pin_memory()
+    probe_sum = 0.0
     for _ in range(K):
         s2.step(st2)
+        # the step's result read back by the host every step (contract: a device -> host read per step): a 4 KB probe
+        # of the freshly updated latent store, a plain blocking D2H copy (no kernel)
+        probe.copy_(st2.latents.view(-1)[:1024])
+        probe_sum += float(probe[0])
+        s2.d2h_bytes += probe.numel() * 4
     torch.cuda.synchronize(dev)
     t2 = time.perf_counter()
     z = s2.end(st2)                                                                       # D2H of the latents

@@ -486,6 +486,15 @@ cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_
   static int pipelined = env_int("CAP4D_GN_PIPELINE", 1);
   void* args[] = {&x1, &x2, &C1, &C2, &hw, &cpg, &rpc, &nch, &n_img, &partial, &stats, &sync, &ticket, &gamma, &beta, &eps,
                   &apply_silu, &out, &raw_out, &x2_G, &x2_V, &x2_R, &pipelined, &out_f16};
+  // CAP4D_GN_COOPERATIVE=0 (experiments only): an ordinary launch of the same grid - every block still fits the GPU at
+  // once, but nothing then guarantees it against other work sharing the device
+  static const int cooperative = env_int("CAP4D_GN_COOPERATIVE", 1);
+  if (!cooperative) {
+    gn_fused_kernel<NQI, UNROLL><<<dim3(grid), block, smem, stream>>>(x1, x2, C1, C2, hw, cpg, rpc, nch, n_img, partial, stats,
+                                                                      sync, ticket, gamma, beta, eps, apply_silu, out,
+                                                                      raw_out, x2_G, x2_V, x2_R, pipelined, out_f16);
+    return cudaGetLastError();
+  }
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_fused_kernel<NQI, UNROLL>), dim3(grid), block,
                                      args, smem, stream);
 }
