@@ -138,6 +138,28 @@ class _CudaBackend:
         st.bufs = {}    # n -> (x_in, z_in, mask, pos, t_in, eps)
         st.graphs = {}  # n -> torch.cuda.CUDAGraph
         st.xchg = None
+        if self.use_cuda_graph:
+            # Capture the call graph of every batch shape this rank will use (full calls and a ragged tail) NOW, so
+            # that step() is replays from its first call on.  A capture needs one eager run first (it builds the
+            # launch plan and sets the kernels' attributes): gather + U-Net on zeroed index tables (row 0 of every
+            # store) - the update kernel, the only one that writes the latent store, is not part of the warm-up.
+            st.dev_block.zero_()
+            st.dev_call.zero_()
+            mine = len(range(st.rank, st.n_its, st.world))
+            shapes = sorted({min(st.gpc, mine)} | ({mine % st.gpc} if mine > st.gpc else set()), reverse=True)
+            for n in shapes:
+                if n > 0:
+                    self._capture(st, n)
+
+    def _capture(self, st, n: int) -> None:
+        with torch.cuda.device(self.device):
+            self._launch_call(st, n, update=False)
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_call(st, n)
+            st.graphs[n] = g
+            self.graphs_captured += 1
 
     # ---- per step ------------------------------------------------------------------------------
     def start_step(self, st, ref_batches: np.ndarray, gen_batches: np.ndarray, step: int, x_f: float, e_f: float,
@@ -177,7 +199,7 @@ class _CudaBackend:
             st.bufs[n] = b
         return b
 
-    def _launch_call(self, st, n: int) -> None:
+    def _launch_call(self, st, n: int, update: bool = True) -> None:
         x_in, z_in, m_in, p_in, t_in, eps = self._buffers(st, n)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         ref_ptr = st.dev_block.data_ptr() if st.R > 0 else None
@@ -188,6 +210,8 @@ class _CudaBackend:
                                                 m_in.data_ptr(), p_in.data_ptr(), t_in.data_ptr(), stream),
             "sampler_gather")
         self.unet.forward_into(x_in, t_in, z_in, m_in, p_in, eps, n_ref_views=st.R)
+        if not update:
+            return
         _lib.check(
             self._lib.cap4d_b200_sampler_update(st.latents.data_ptr(), eps.data_ptr(), gen_ptr, st.dev_call.data_ptr(), n,
                                                 st.V, st.R, st.chw, st.cfg_scale, stream),
@@ -206,16 +230,8 @@ class _CudaBackend:
                 self._launch_call(st, n)
                 return
             g = st.graphs.get(n)
-            if g is None:
-                self._launch_call(st, n)  # eager first: builds the launch plan, sets kernel attributes
-                torch.cuda.current_stream(self.device).synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch_call(st, n)
-                st.graphs[n] = g
-                self.graphs_captured += 1
-                # the eager run above already applied this call's update: restore nothing - the capture itself
-                # launches no work, so the step's arithmetic ran exactly once
+            if g is None:  # a shape begin() did not foresee: run it from the host
+                self._launch_call(st, n)
                 return
             g.replay()
             self.unet._calls += 1

@@ -147,8 +147,8 @@ def test_sampler_graph_replay_is_bit_identical_and_uploads_no_zeros(cuda_device)
         s = B200StochasticIOSampler(model, groups_per_call=2, use_cuda_graph=graphs)
         outs[graphs] = s.sample(**kw)
         if graphs:
-            # 5 groups in calls of 2 + 2 + 1: two batch shapes, each captured once and replayed afterwards
-            assert s.backend.graphs_captured == 2 and s.backend.graph_replays == 3 * 4 - 2
+            # 5 groups in calls of 2 + 2 + 1: two batch shapes, both captured in begin(); every call is a replay
+            assert s.backend.graphs_captured == 2 and s.backend.graph_replays == 3 * 4
             cond_bytes = sum(t.numel() * 4 for d in (rc, gc) for t in d.values())
             x_bytes = 15 * 4 * 8 * 8 * 4
             step_bytes = 4 * ((5 * 1 + 5 * 3) * 8 + 3 * ctypes.sizeof(__import__("cap4d_b200")._lib.SamplerCall))
