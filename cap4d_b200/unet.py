@@ -243,6 +243,7 @@ class B200MMDMUnet(torch.nn.Module):
         self._ensure_built()
         n = ctypes.c_int()
         with torch.cuda.device(self._device):
+            torch.cuda.synchronize(self._device)  # forwards may run on non-blocking streams the library's read cannot see
             _lib.check(self._lib.cap4d_b200_unet_ref_view_violations(self._handle, ctypes.byref(n)), "ref_view_violations")
         return n.value
 

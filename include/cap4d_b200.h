@@ -82,7 +82,8 @@ int cap4d_b200_unet_set_ref_views(void* handle, int n_ref_views);
 
 /* The promise is checked on the device: a view declared a reference view whose ref_mask is 0 was never
  * computed, so its output is written as NaN (never a silently wrong number) and counted.  Returns the number of
- * such views since the last call and resets the count; synchronises with the device. */
+ * such views since the last call and resets the count.  Blocking read on the legacy default stream: synchronise
+ * non-blocking streams that ran forwards first. */
 int cap4d_b200_unet_ref_view_violations(void* handle, int* n);
 
 /* Scratch needed by one forward at this shape (caller owns the buffer; >= 1024 B aligned). */
