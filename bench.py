@@ -319,7 +319,7 @@ def _gemm_traffic(gpc, workload):
             d = json.load(f)
     except Exception:
         return None, "no ncu capture of bench.py (scripts/ncu_bench_traffic.sh)"
-    if d.get("source_digest") != _build._digest():
+    if d.get("source_digest") != _build.kernel_digest():
         return None, f"{os.path.relpath(path, ROOT)} is stale: captured with other kernel sources"
     if d.get("groups_per_call") != gpc or d.get("workload") != workload:
         return None, f"{os.path.relpath(path, ROOT)} was captured for another batch shape / workload"

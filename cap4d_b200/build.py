@@ -41,6 +41,17 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def kernel_digest() -> str:
+    """Digest of what decides the generated kernels (csrc/ sources, headers and flags; not the C-ABI header): the
+    stamp on ncu captures that bench.py compares before it quotes them."""
+    h = hashlib.sha256()
+    for f in SOURCES + [x for x in HEADERS if not x.startswith("..")]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = True) -> str:
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):

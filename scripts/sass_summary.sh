@@ -5,7 +5,7 @@
 #   scripts/sass_summary.sh > profiles/r02_sass_summary.txt
 cd "$(dirname "$0")/.." || exit 1
 LIB=cap4d_b200/libcap4d_b200.so
-echo "# cuobjdump -sass $LIB ($(sha256sum $LIB | cut -c1-16)), source digest $(python -c 'from cap4d_b200 import build; print(build._digest()[:16])')"
+echo "# cuobjdump -sass $LIB ($(sha256sum $LIB | cut -c1-16)), source digest $(python -c 'from cap4d_b200 import build; print(build.kernel_digest()[:16])')"
 printf "%-44s %8s %8s %6s %6s %7s %8s %7s %6s\n" kernel UTC*MMA UTMALDG LDTM STTM UTCBAR MUFU.EX2 FFMA2 HMMA
 cuobjdump -sass "$LIB" 2>/dev/null | c++filt | awk '
   /Function :/ { if (name != "") emit(); name=$0; sub(/.*Function : /, "", name); mma=tma=ld=st=bar=ex2=f2=h=0; next }

@@ -45,7 +45,7 @@ for name, v in sorted(per.items(), key=lambda kv: -kv[1].get("gpu__time_duration
 out = {"what": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over bench.py "
                "(scripts/ncu_bench_traffic.sh): launches of the first U-Net calls of the timed region, cold-cache and "
                "serialised (compare shares, not absolutes)",
-       "source_digest": B._digest(), "groups_per_call": gpc, "workload": workload, "n_launches": sum(len(s) for s in launch_ids.values()),
+       "source_digest": B.kernel_digest(), "groups_per_call": gpc, "workload": workload, "n_launches": sum(len(s) for s in launch_ids.values()),
        "library_kernels": sorted(k for k in kernels if k.startswith("at::") or "at::native" in k or "elementwise_kernel" in k or "vectorized_" in k or "cutlass" in k or "cudnn" in k),
        "kernels": kernels}
 with open(dst, "w") as fh:
