@@ -34,18 +34,30 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
 namespace {
 
 constexpr int BQ = 128;   // query rows per softmax warpgroup (one UMMA M tile)
-constexpr int NQT = 2;    // Q tiles per CTA
+#ifndef CAP4D_ATTN_NQT
+#define CAP4D_ATTN_NQT 2  // Q tiles per CTA.  1 (A/B builds): half the TMEM, threads and shared memory, two CTAs per SM
+#endif
+constexpr int NQT = CAP4D_ATTN_NQT;    // Q tiles per CTA
+static_assert(NQT == 1 || NQT == 2, "one or two Q tiles per CTA");
 constexpr int BKV = 128;  // keys per tile
 constexpr int HD = 64;    // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KiB: one Q / K / V tile
-constexpr int KS = 4, VS = 4;
-constexpr int ATTN_THREADS = 640;         // WG0: TMA / MMA / TMEM owner; WG1-2: softmax of Q tile A; WG3-4: Q tile B
+#ifndef CAP4D_ATTN_KS
+#define CAP4D_ATTN_KS (NQT == 2 ? 4 : 3)
+#endif
+#ifndef CAP4D_ATTN_VS
+#define CAP4D_ATTN_VS (NQT == 2 ? 4 : 2)
+#endif
+constexpr int KS = CAP4D_ATTN_KS, VS = CAP4D_ATTN_VS;  // K / V ring depths (NQT == 1: two CTAs share the SM's 227 KB)
+constexpr int ATTN_THREADS = 128 + NQT * 256;  // WG0: TMA / MMA / TMEM owner; WG1-2: softmax of Q tile A; WG3-4: Q tile B
+constexpr int CTAS_PER_SM = (NQT == 2) ? 1 : 2;
+constexpr int LAUNCH_REGS = (NQT == 2) ? 96 : 80;  // what ptxas gives every thread under the launch bounds
 constexpr int SPLIT = 2;                  // threads per query row: each owns BKV / SPLIT keys of every tile
 constexpr int HK = BKV / SPLIT;           // keys per softmax thread and tile
-constexpr int TM_COLS = 512;
-constexpr int TM_S = 0;     // S_X (fp32 128x128)   at   0 + 128 x
-constexpr int TM_O = 256;   // O_X (fp32 128x64)    at 256 +  64 x
-constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
+constexpr int TM_COLS = NQT * 256;
+constexpr int TM_S = 0;                    // S_X (fp32 128x128)   at   0 + 128 x
+constexpr int TM_O = NQT * 128;            // O_X (fp32 128x64)    behind the S tiles, + 64 x
+constexpr int TM_P = NQT * 128 + NQT * 64; // P_X (bf16 128x128 = 64 columns) behind the O tiles, + 64 x
 // pool = 640 * 96 at launch: 128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96) or the kernel deadlocks.
 // Overridable for A/B builds (scripts/attn_variants.sh): -DCAP4D_ATTN_REGS_CTRL=32 -DCAP4D_ATTN_REGS_SOFTMAX=112
 #ifndef CAP4D_ATTN_PACKED_F32X2
@@ -54,8 +66,14 @@ constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
 #ifndef CAP4D_ATTN_POLY_EVERY
 #define CAP4D_ATTN_POLY_EVERY 0  // needs CAP4D_ATTN_PACKED_F32X2: every N-th pair of scores uses exp2_poly_pair
 #endif
+#ifndef CAP4D_ATTN_LD64
+#define CAP4D_ATTN_LD64 0   // A/B builds: one tcgen05.ld x64 per tile instead of two x32
+#endif
+#ifndef CAP4D_ATTN_MAX4
+#define CAP4D_ATTN_MAX4 1   // four row-max chains instead of two (+0.7-0.9 %, profiles/r02_attn_micro2.log); 0 = round-1 code
+#endif
 #ifndef CAP4D_ATTN_REGS_CTRL
-#define CAP4D_ATTN_REGS_CTRL 40
+#define CAP4D_ATTN_REGS_CTRL (NQT == 2 ? 40 : 32)
 #endif
 #ifndef CAP4D_ATTN_REGS_SOFTMAX
 #define CAP4D_ATTN_REGS_SOFTMAX 104
@@ -71,7 +89,7 @@ constexpr int TM_P = 384;   // P_X (bf16 128x128 = 64 columns) at 384 + 64 x
 #endif
 constexpr int REGS_CTRL = CAP4D_ATTN_REGS_CTRL, REGS_SOFTMAX = CAP4D_ATTN_REGS_SOFTMAX;
 static_assert(REGS_CTRL % 8 == 0 && REGS_SOFTMAX % 8 == 0 && REGS_CTRL >= 24 && REGS_SOFTMAX <= 256 &&
-                  128 * (96 - REGS_CTRL) >= 512 * (REGS_SOFTMAX - 96),
+                  128 * (LAUNCH_REGS - REGS_CTRL) >= NQT * 256 * (REGS_SOFTMAX - LAUNCH_REGS),
               "setmaxnreg budget: the control warpgroup must release what the softmax warpgroups take");
 constexpr float RESCALE_LOG2 = 8.0f;  // O / l are only rescaled when the row max grew by more than 2^8
 
@@ -142,8 +160,12 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
   float s[HK];
   {
     uint32_t* su = reinterpret_cast<uint32_t*>(s);
+#if CAP4D_ATTN_LD64
+    tmem_ld64(s_addr, su);
+#else
     tmem_ld32(s_addr, su);
     tmem_ld32(s_addr + 32, su + 32);
+#endif
     tmem_ld_wait();
   }
   tc_fence_before();
@@ -158,6 +180,17 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
   bool pv_waited = (j == 0);
   if (j == 0) m_used = 0.f;
 #else
+#if CAP4D_ATTN_MAX4
+  float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
+#pragma unroll
+  for (int i = 8; i < HK; i += 8) {
+    mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+    mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+    mx2 = fmaxf(mx2, fmaxf(s[i + 4], s[i + 5]));
+    mx3 = fmaxf(mx3, fmaxf(s[i + 6], s[i + 7]));
+  }
+  const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+#else
   float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
   for (int i = 4; i < HK; i += 4) {
@@ -165,6 +198,7 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
   }
   const float m_half = fmaxf(mx0, mx1);
+#endif
   float* xc = &bars->xchg[j & 1][x][0][0];
   xc[half * BQ + r] = m_half;
   named_bar_sync(1 + x * 4 + (r >> 5), 64);  // the two warps that share these 32 rows
@@ -247,7 +281,7 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
 }
 
 template <bool TRACE>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -308,7 +342,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * p.C + head * HD, row_base + j * BKV);
       }
-    } else if ((warp == 1 || warp == 3) && lane == 0) {
+    } else if ((warp == 1 || (warp == 3 && NQT == 2)) && lane == 0) {
       // ===================== MMA issuers: warp 1 -> Q tile A, warp 3 -> Q tile B =====================
       // (one issuing thread per Q tile: the mbarrier round trips of one tile's chain do not delay the other's)
       const int x = warp >> 1;
@@ -368,7 +402,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     // Tile B's softmax warps start about half a tile late: the two tiles then tend to alternate on the MUFU pipe
     // (one exponentiates while the other loads / takes its max / stores P) instead of running in lockstep.
     // Measured -3 % on the large shapes; enforcing the alternation with named barriers costs 10 % instead.
-    if (x == 1) __nanosleep(600);
+    if (NQT == 2 && x == 1) __nanosleep(600);
     const int valid_last = p.L - (nkv - 1) * BKV;  // valid keys in the last tile (1..128)
 
     // the key mask costs 2 ALU ops per score, so it is compiled only into the (peeled) last tile
