@@ -69,6 +69,12 @@ constexpr int TM_P = NQT * 128 + NQT * 64; // P_X (bf16 128x128 = 64 columns) be
 #ifndef CAP4D_ATTN_LD64
 #define CAP4D_ATTN_LD64 0   // A/B builds: one tcgen05.ld x64 per tile instead of two x32
 #endif
+#ifndef CAP4D_ATTN_ST_SPLIT
+#define CAP4D_ATTN_ST_SPLIT 0   // A/B builds: P leaves in two x16 stores, the first one behind the first 32 exponentials
+#endif
+#ifndef CAP4D_ATTN_B_DELAY_NS
+#define CAP4D_ATTN_B_DELAY_NS 1500  // head start of Q tile A's softmax warps over tile B's (sweep: profiles/r02_attn_delay.log)
+#endif
 #ifndef CAP4D_ATTN_MAX4
 #define CAP4D_ATTN_MAX4 1   // four row-max chains instead of two (+0.7-0.9 %, profiles/r02_attn_micro2.log); 0 = round-1 code
 #endif
@@ -235,19 +241,21 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     f32x2 rs2 = pack2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < HK; i += 2) {
-      float a0, a1, p0, p1;
+      float a0, a1;
       unpack2(fma2(pack2(s[i], s[i + 1]), sc2, nm2), a0, a1);
-#if CAP4D_ATTN_POLY_EVERY > 0
-      if (((i >> 1) % CAP4D_ATTN_POLY_EVERY) == CAP4D_ATTN_POLY_EVERY - 1) {
-        exp2_poly_pair(a0, a1, p0, p1);  // this pair's exponentials on the FMA pipe instead of the MUFU
-      } else
-#endif
-      {
-        p0 = ex2f(a0);
-        p1 = ex2f(a1);
-      }
+      const float p0 = ex2f(a0), p1 = ex2f(a1);
       rs2 = add2(rs2, pack2(p0, p1));
       pk[i >> 1] = pack_bf16x2(p0, p1);
+#if CAP4D_ATTN_ST_SPLIT
+      if (i == HK / 2 - 2) {  // the first half of this thread's P columns is complete
+        if (!pv_waited) {
+          mbar_wait(&bars->pv_full[x], (j - 1) & 1);
+          tc_fence_after();
+          pv_waited = true;
+        }
+        tmem_st16(p_addr, pk);
+      }
+#endif
     }
     float rs0, rs1;
     unpack2(rs2, rs0, rs1);
@@ -272,7 +280,11 @@ __device__ __forceinline__ void softmax_tile(AttnBars* bars, int x, int half, in
     tc_fence_after();
   }
   // P_X(j) -> TMEM as the A operand of the PV MMA: lane = query row, column c = keys (2c, 2c+1) as bf16x2
+#if CAP4D_ATTN_ST_SPLIT && CAP4D_ATTN_PACKED_F32X2
+  tmem_st16(p_addr + HK / 4, pk + HK / 4);
+#else
   tmem_st32(p_addr, pk);
+#endif
   tmem_st_wait();
   ATTN_STAMP(5);
   tc_fence_before();
@@ -402,7 +414,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     // Tile B's softmax warps start about half a tile late: the two tiles then tend to alternate on the MUFU pipe
     // (one exponentiates while the other loads / takes its max / stores P) instead of running in lockstep.
     // Measured -3 % on the large shapes; enforcing the alternation with named barriers costs 10 % instead.
-    if (NQT == 2 && x == 1) __nanosleep(600);
+    if (NQT == 2 && x == 1 && CAP4D_ATTN_B_DELAY_NS > 0) __nanosleep(CAP4D_ATTN_B_DELAY_NS);
     const int valid_last = p.L - (nkv - 1) * BKV;  // valid keys in the last tile (1..128)
 
     // the key mask costs 2 ALU ops per score, so it is compiled only into the (peeled) last tile
