@@ -106,6 +106,7 @@ struct AttnPlan {
   CUtensorMap tmQKV;
   int M, C, L, n_seq, heads;
   bf16* out;
+  const bf16* qkv;
   float scale_log2;  // softmax scale * log2(e)
   dim3 grid;
   size_t smem_bytes;

@@ -219,6 +219,31 @@ def test_attention(ops, cuda_device, n_seq, L, C):
     assert float((out.double() - ref).norm() / ref.norm()) < 5e-3
 
 
+@pytest.mark.parametrize("L,slope,spike", [(1024, 1.5, 0.0), (1024, 0.0, 20.0), (1000, 0.4, 25.0), (200, 0.0, 30.0)])
+def test_attention_logits_that_outgrow_the_first_tile(ops, cuda_device, L, slope, spike):
+    # the kernel takes the exact row max at KV tile 0 only and follows later growth through the row sums
+    # (attn_tc.cu, rq_regrow): logits that climb by ~17 octaves per tile (slope) exercise the power-of-two
+    # shift, a late key ~100+ nats above everything before it (spike) the recomputation from global memory.
+    # legacy_attention's softmax (attention.py:125) is exact for both.
+    g = torch.Generator().manual_seed(L + int(10 * slope) + int(spike))
+    C = 128
+    base = torch.randn(1, C, generator=g)
+    base = base / base.reshape(2, 64).norm(dim=1).repeat_interleave(64) * 8.0   # |base_h|^2 = 64 per head
+    q = base + 0.1 * torch.randn(L, C, generator=g)
+    tile = (torch.arange(L) // 128).float().unsqueeze(1)
+    k = torch.randn(L, C, generator=g) * 0.5 + slope * tile * base
+    if spike:
+        k[L - 5] = spike * base[0]
+        k[L // 2 + 3] = 0.5 * spike * base[0]
+    v = torch.randn(L, C, generator=g)
+    qkv = torch.cat([q, k, v], dim=1).to(cuda_device).to(torch.bfloat16)
+    out = ops.attention(qkv, C, L)
+    ref = _attn_ref(qkv, C, L)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 1e-2
+    assert float((out.double() - ref).norm() / ref.norm()) < 5e-3
+
+
 def test_attention_is_key_permutation_invariant(ops, cuda_device):
     # the "3d" rearrange '(b t) n (h d) -> (b h) (n t) d' only permutes tokens inside a sequence
     g = torch.Generator().manual_seed(5)
