@@ -52,6 +52,10 @@ struct SmemTail {
   uint32_t tmem_base;
 };
 
+// EPI == 1 (residual GEMMs): one 32 x 32 fp32 transpose buffer per epilogue warp behind the barriers
+constexpr int EPI_BUF_OFFSET = (static_cast<int>(sizeof(SmemTail)) + 127) & ~127;
+constexpr int EPI_BUF_BYTES = 8 * 32 * 32 * 4;
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -114,8 +118,10 @@ __device__ __forceinline__ int up_row(int row, int H, int W, int py, int px) {
 // A CTA tile is (msub * 128) x BN: msub in {1, 2} 128-row sub-tiles share one B (weight) tile per k-block,
 // which raises the FLOPs per byte streamed from L2 - the resource this kernel is bound by - from
 // 2*128*BN*64 / (16K + 128 BN) to 2*256*BN*64 / (32K + 128 BN).
-// EPI = 1: plain GEMM + fp32 residual (no conv operand, no GEGLU, no per-image bias): its own instantiation so
+// EPI = 1, 2: plain GEMM + fp32 residual (no conv operand, no GEGLU, no per-image bias): their own instantiations so
 // that the residual look-ahead buffers below do not disturb the register allocation of the generic epilogue.
+// 2 = the HBM-bound shapes (short K: to_out / proj_out, FF2 at C = 320), coalescing epilogue through shared memory;
+// 1 = the tensor-bound ones (row-per-thread accesses, no shared-memory buffer: one more pipeline stage).
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -128,6 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * a_stage_bytes;
   SmemTail* tail = reinterpret_cast<SmemTail*>(sB + p.stages * b_stage_bytes);
+  float* epi_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + EPI_BUF_OFFSET);  // EPI == 1 only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,7 +284,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_phase = (p.n_acc == 2) ? ((it >> 1) & 1) : (it & 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
       auto chunk_col = [&](int cc) { return (cc / cps) * p.BN + (cc % cps) * tcols; };  // TMEM column of chunk cc
-      if constexpr (EPI == 1) {
+      if constexpr (EPI == 2) {
+        // Plain GEMM + fp32 residual (to_out, FF2, proj_out: K is short, the kernel IS its epilogue).  A thread
+        // owns an accumulator ROW, and row-per-thread global accesses cost one L1 wavefront per thread and
+        // instruction (ncu, round 2: LSU wavefronts 62 % of peak - the busiest unit of the launch - with DRAM at
+        // 48 %).  So the accumulator chunk (32 rows x 32 columns per warp) goes through a swizzled 4 KB
+        // shared-memory buffer into the coalesced layout - eight threads per row, four rows per instruction:
+        // 4 lines per request instead of 32 - in which the residual is read and the result written.  The residual
+        // does not depend on the accumulator: chunk cc+1's is requested before chunk cc is read from TMEM (the
+        // first one before the tile's MMAs have finished): two buffers, used alternately.
+        float* tb = epi_buf + (warp - EPI_WARP0) * 1024;
+        const int lr = lane >> 3, lc = lane & 7;  // coalesced layout: element i = row 4 i + lr, columns 4 lc .. 4 lc + 3
+        float4 r0[8], r1[8];
+        // (sub, c) of the chunk in hand and of the next one, advanced without dividing
+        int sub = c_begin / cps, c = c_begin - sub * cps;
+        const int row_warp = m_tile * p.msub * BM + q * 32;
+        const float* res_col = p.residual + n_tile * p.BN + lc * 4;
+        auto res_load = [&](int sb, int ch, float4(&r)[8]) {
+          const int rb = row_warp + sb * BM + lr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (rb + 4 * i < p.M)
+              r[i] = __ldg(reinterpret_cast<const float4*>(res_col + static_cast<size_t>(rb + 4 * i) * p.ldr + ch * 32));
+        };
+        if (c_begin < c_end) res_load(sub, c, r0);
+        mbar_wait(&tail->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        if (c_begin < c_end) tmem_ld32(taddr + sub * p.BN + c * 32, v);
+        auto process = [&](int cc, float4(&cur)[8], float4(&nxt)[8]) {
+          int sub_n = sub, c_n = c + 1;
+          if (c_n == cps) {
+            c_n = 0;
+            ++sub_n;
+          }
+          const bool more = cc + 1 < c_end;
+          if (more) res_load(sub_n, c_n, nxt);
+          tmem_ld_wait();
+          // own row -> buffer; 16 B pieces XOR-swizzled by the row so that both directions are conflict-free
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          if (more) tmem_ld32(taddr + sub_n * p.BN + c_n * 32, v);
+          __syncwarp();
+          const int col0 = n_tile * p.BN + c * 32 + lc * 4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0));
+          const int rb = row_warp + sub * BM + lr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + lr;
+            float4 a = *reinterpret_cast<const float4*>(tb + rl * 32 + ((lc ^ (rl & 7)) << 2));
+            if (rb + 4 * i < p.M) {
+              // (acc + residual) + bias, the order of every other epilogue: all tile configurations stay bit-identical
+              a.x = (a.x + cur[i].x) + bv.x, a.y = (a.y + cur[i].y) + bv.y;
+              a.z = (a.z + cur[i].z) + bv.z, a.w = (a.w + cur[i].w) + bv.w;
+              const size_t off = static_cast<size_t>(rb + 4 * i) * p.ldo + col0;
+              if ((p.out_mode & 15) == OUT_F32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = a;
+              } else {
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) =
+                    make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              }
+            }
+          }
+          __syncwarp();  // the buffer is rewritten by the next chunk
+          sub = sub_n;
+          c = c_n;
+        };
+        for (int cc = c_begin; cc < c_end; cc += 2) {
+          process(cc, r0, r1);
+          if (cc + 1 < c_end) process(cc + 1, r1, r0);
+        }
+      } else if constexpr (EPI == 1) {
         // Plain GEMM + fp32 residual (to_out, FF2, proj_out: K is short, the kernel IS its epilogue, and ncu
         // shows it waiting on the residual rows: ~4 KB in flight per warp).  The residual does not depend on
         // the accumulator, so chunk cc+1's row segment is requested before chunk cc is even read from TMEM
@@ -742,6 +822,23 @@ TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
 }
 
 // Derive everything that depends on the tile configuration: tile counts, smem ring, grid, weight tensor map.
+// which problems take the EPI = 1 instantiation (see gemm_tc_kernel)
+bool residual_lookahead(const GemmParams& p) {
+  static const bool off = getenv("CAP4D_GEMM_NO_LOOKAHEAD") != nullptr;
+  return !off && p.residual != nullptr && !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 &&
+         p.rowbias == nullptr && p.up_py < 0;
+}
+// 0: generic epilogue, 1: residual look-ahead, 2: residual look-ahead + coalescing epilogue.  FLOPs per algorithmic
+// byte below the HBM ridge (measured: 4.2 -> 4.6-5.0 TB/s on the K = C shapes, profiles/r02b_residual_gemm.log; the
+// K = 4C shapes at C >= 640 are tensor-bound and lose a pipeline stage to the 32 KB buffer).  CAP4D_GEMM_EPI forces.
+int epilogue_kind(const GemmParams& p, int N, int Ktot) {
+  if (!residual_lookahead(p)) return 0;
+  static const char* force = getenv("CAP4D_GEMM_EPI");
+  if (force != nullptr && (force[0] == '1' || force[0] == '2')) return force[0] - '0';
+  const double intensity = 2.0 * N * Ktot / (2.0 * Ktot + 8.0 * N);
+  return intensity < 200.0 ? 2 : 1;
+}
+
 bool apply_cfg(GemmPlan* plan, const TileCfg& cfg, const bf16* Wt, int N, int Ktot) {
   GemmParams& p = plan->p;
   const int bn = cfg.bn;
@@ -755,11 +852,13 @@ bool apply_cfg(GemmPlan* plan, const TileCfg& cfg, const bf16* Wt, int N, int Kt
   p.tiles_n = N / bn;
   p.num_kb = Ktot / BK;
   const int stage_bytes = cfg.two_cta ? (A_SUB_BYTES + (bn / 2) * BK * 2) : (cfg.msub * A_SUB_BYTES + bn * BK * 2);
-  int stages = (220 * 1024 - static_cast<int>(sizeof(SmemTail)) - 1024) / stage_bytes;
+  p.epi = cfg.two_cta ? 0 : epilogue_kind(p, N, Ktot);
+  const int epi_extra = p.epi == 2 ? EPI_BUF_OFFSET + EPI_BUF_BYTES : 0;
+  int stages = (220 * 1024 - static_cast<int>(sizeof(SmemTail)) - 1024 - epi_extra) / stage_bytes;
   stages = std::min(stages, MAX_STAGES);
   stages = std::min(stages, std::max(2, p.num_kb));
   p.stages = stages;
-  plan->smem_bytes = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemTail) + 1024;
+  plan->smem_bytes = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemTail) + 1024 + epi_extra;
   plan->grid = cfg.two_cta ? 2 * std::min(p.tiles_m * p.tiles_n, std::max(1, sm_count() / 2))
                            : std::min(p.tiles_m * p.tiles_n, sm_count());
   // weights: [N][Ktot] row-major
@@ -926,9 +1025,9 @@ bool make_gemm_plan(GemmPlan* plan, const bf16* A, int M, int K, const bf16* A2,
     plan->tmA2 = plan->tmA;
     K2 = 0;
   }
+  p.up_py = p.up_px = -1;  // before finish_plan: apply_cfg sizes shared memory by the epilogue the launch will pick
   if (!finish_plan(plan, Wt, N, K + K2, out_mode, out, ldo, bias, rowbias, rowbias_div, rowbias_ld, residual, ldr))
     return false;
-  p.up_py = p.up_px = -1;
   return autotune(plan, Wt, N, K + K2);
 }
 
@@ -1029,13 +1128,6 @@ bool make_conv_plan(GemmPlan* plan, const bf16* A, const ConvGeom& g, int Cin, c
   return autotune(plan, Wt, N, ntaps * Cin + K2);
 }
 
-// which problems take the EPI = 1 instantiation (see gemm_tc_kernel)
-static bool residual_lookahead(const GemmParams& p) {
-  static const bool off = getenv("CAP4D_GEMM_NO_LOOKAHEAD") != nullptr;
-  return !off && p.residual != nullptr && !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 &&
-         p.rowbias == nullptr && p.up_py < 0;
-}
-
 cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   // the attribute is per device: one flag per device ordinal (several executors of one process may sit on
   // different GPUs, e.g. the reference's device_model_map)
@@ -1048,13 +1140,17 @@ cudaError_t launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     if (known) attr_set[dev].store(true, std::memory_order_release);
   }
   if (plan.two_cta)
     gemm_tc_2sm_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
-  else if (residual_lookahead(plan.p))
+  else if (plan.p.epi == 2)
+    gemm_tc_kernel<2><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
+  else if (plan.p.epi == 1)
     gemm_tc_kernel<1><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);
   else
     gemm_tc_kernel<0><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.tmA, plan.tmA2, plan.tmB, plan.p);

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Residual-epilogue GEMMs of the transformer blocks (to_out / proj_out: K = C, fp32 out; FF2: K = 4C, bf16 out) at the
+production shapes of a 5-group call: time, algorithmic bytes per second and FLOP/s.
+    python scripts/bench_residual_gemm.py [lib.so ...]      (no argument: the product library)"""
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SHAPES = [  # (M, C): 10 x 8 views x 64^2, 32^2, 16^2 tokens; generated views only (10 x 7) at level 0 of the up path
+    (327680, 320), (286720, 320), (81920, 640), (20480, 1280)]
+
+
+def run_one():
+    import torch
+    from cap4d_b200 import ops
+    dev = torch.device("cuda:0")
+    rows = []
+    for M, C in SHAPES:
+        for K, mode, name in ((C, ops.OUT_F32, "to_out/proj_out"), (4 * C, ops.OUT_BF16, "ff2")):
+            g = torch.Generator().manual_seed(1)
+            a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+            w = (torch.randn(C, K, device=dev) / math.sqrt(K)).to(torch.bfloat16)
+            bias = torch.randn(C, device=dev)
+            res = torch.randn(M, C, device=dev)
+            _, ms = ops.gemm(a, w, bias=bias, residual=res, out_mode=mode, time_iters=10)
+            nbytes = M * K * 2 + M * C * 4 + M * C * (4 if mode == ops.OUT_F32 else 2)
+            rows.append({"op": name, "M": M, "N": C, "K": K, "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1),
+                         "TFLOPs": round(2.0 * M * C * K / ms / 1e9, 1)})
+    return rows
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--child":
+        print(json.dumps(run_one()))
+        sys.exit(0)
+    libs = sys.argv[1:] or [None]
+    prod = os.path.join(ROOT, "cap4d_b200", "libcap4d_b200.so")
+    keep = prod + ".keep"
+    shutil.copy(prod, keep)
+    try:
+        for lib in libs:
+            if lib:
+                shutil.copy(lib, prod)
+            out = subprocess.run([sys.executable, __file__, "--child"], capture_output=True, text=True)
+            print("==", lib or "product library")
+            if out.returncode != 0:
+                print(out.stderr[-2000:])
+                continue
+            for r in json.loads(out.stdout.strip().splitlines()[-1]):
+                print(json.dumps(r))
+    finally:
+        shutil.move(keep, prod)

@@ -77,6 +77,25 @@ def test_gemm_no_epilogue_and_bf16_out(ops, cuda_device):
     assert _rel(out16.float(), ref) < 4e-3  # one bf16 rounding of the output (2^-9 relative)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 320, 1280), (4096, 640, 640), (77, 64, 64)])
+def test_gemm_residual_epilogue_bf16_and_f32(ops, cuda_device, M, N, K):
+    """to_out / FF2 / proj_out (attention.py:311-326): GEMM + bias + fp32 residual through the coalescing epilogue
+    (accumulator chunk transposed in shared memory), fp32 and bf16 outputs, ragged M."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_device).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res = (3.0 * torch.randn(M, N, generator=g)).to(cuda_device)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    out = ops.gemm(a, w, bias=bias, residual=res)
+    assert _rel(out, ref) < 2e-5
+    out16 = ops.gemm(a, w, bias=bias, residual=res, out_mode=ops.OUT_BF16)
+    assert out16.dtype == torch.bfloat16
+    assert _rel(out16.float(), ref) < 4e-3
+    out_nb = ops.gemm(a, w, residual=res)
+    assert _rel(out_nb, ref - bias.double()) < 2e-5
+
+
 def test_gemm_geglu(ops, cuda_device):
     # attention.py:68-75: x, gate = proj(x).chunk(2); x * gelu(gate)   (exact erf GELU)
     g = torch.Generator().manual_seed(2)
