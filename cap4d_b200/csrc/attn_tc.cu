@@ -90,6 +90,9 @@ constexpr int TM_P = NQT * 128 + NQT * 64; // P_X (bf16 128x128 = 64 columns) be
 #ifndef CAP4D_ATTN_TURNS
 #define CAP4D_ATTN_TURNS 0   // row-quad variant: the two Q tiles take turns on each scheduler's MUFU (exp(j) of A, exp(j) of B, exp(j+1) of A, ...)
 #endif
+#ifndef CAP4D_ATTN_EARLY_TMA
+#define CAP4D_ATTN_EARLY_TMA 0   // Q, K(0), V(0) requested before the TMEM allocation / first block barrier
+#endif
 #ifndef CAP4D_ATTN_LAZYMAX
 #define CAP4D_ATTN_LAZYMAX 0   // row-quad variant: exact row max at KV tile 0 only, growth detected through the row sums (softmax_tile_rq)
 #endif
@@ -666,6 +669,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       for (int k = 0; k < 4; ++k) mbar_init(&bars->turn[i][k], 2);
     fence_mbar_init();
     mbar_arrive(&bars->always);
+#if CAP4D_ATTN_EARLY_TMA
+    // Q and the first K / V tiles are requested before the TMEM allocation and the block-wide barrier below: their
+    // latency is most of a CTA's start-up, and nothing they touch depends on either
+    mbar_arrive_expect_tx(&bars->q_full, NQT * TILE_BYTES);
+    for (int x = 0; x < NQT; ++x)
+      tma_load_2d(sQ + x * TILE_BYTES, &tmQKV, &bars->q_full, head * HD, row_base + q0 + x * BQ);
+    mbar_arrive_expect_tx(&bars->k_full[0], TILE_BYTES);
+    tma_load_2d(sK, &tmQKV, &bars->k_full[0], p.C + head * HD, row_base);
+    mbar_arrive_expect_tx(&bars->v_full[0], TILE_BYTES);
+    tma_load_2d(sV, &tmQKV, &bars->v_full[0], 2 * p.C + head * HD, row_base);
+#endif
   }
   if (warp == 2) {
     tmem_alloc(&bars->tmem_base, TM_COLS);
@@ -680,10 +694,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     setmaxnreg_dec<REGS_CTRL>();
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer =====================
+#if !CAP4D_ATTN_EARLY_TMA
       mbar_arrive_expect_tx(&bars->q_full, NQT * TILE_BYTES);
       for (int x = 0; x < NQT; ++x)
         tma_load_2d(sQ + x * TILE_BYTES, &tmQKV, &bars->q_full, head * HD, row_base + q0 + x * BQ);
-      for (int j = 0; j < nkv; ++j) {
+#endif
+      for (int j = CAP4D_ATTN_EARLY_TMA ? 1 : 0; j < nkv; ++j) {
         const int ks = j % KS, vs = j % VS;
         mbar_wait(&bars->k_empty[ks], ((j / KS) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);

@@ -293,19 +293,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 4 lines per request instead of 32 - in which the residual is read and the result written.  The residual
         // does not depend on the accumulator: chunk cc+1's is requested before chunk cc is read from TMEM (the
         // first one before the tile's MMAs have finished): two buffers, used alternately.
-        float* tb = epi_buf + (warp - EPI_WARP0) * 1024;
+        const uint32_t tb = smem_u32(epi_buf) + (warp - EPI_WARP0) * 4096;  // this warp's 32 x 32 fp32 buffer
         const int lr = lane >> 3, lc = lane & 7;  // coalesced layout: element i = row 4 i + lr, columns 4 lc .. 4 lc + 3
         float4 r0[8], r1[8];
         // (sub, c) of the chunk in hand and of the next one, advanced without dividing
         int sub = c_begin / cps, c = c_begin - sub * cps;
         const int row_warp = m_tile * p.msub * BM + q * 32;
         const float* res_col = p.residual + n_tile * p.BN + lc * 4;
+        const bool has_res = p.residual != nullptr;  // proj_in takes this epilogue without one
         auto res_load = [&](int sb, int ch, float4(&r)[8]) {
           const int rb = row_warp + sb * BM + lr;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (rb + 4 * i < p.M)
+          for (int i = 0; i < 8; ++i) {
+            r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && rb + 4 * i < p.M)
               r[i] = __ldg(reinterpret_cast<const float4*>(res_col + static_cast<size_t>(rb + 4 * i) * p.ldr + ch * 32));
+          }
         };
         if (c_begin < c_end) res_load(sub, c, r0);
         mbar_wait(&tail->tmem_full[acc], acc_phase);
@@ -324,18 +327,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // own row -> buffer; 16 B pieces XOR-swizzled by the row so that both directions are conflict-free
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<uint4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2)) =
-                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            st_shared_v4(tb + lane * 128 + ((k ^ (lane & 7)) << 4), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           if (more) tmem_ld32(taddr + sub_n * p.BN + c_n * 32, v);
           __syncwarp();
           const int col0 = n_tile * p.BN + c * 32 + lc * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0));
           const int rb = row_warp + sub * BM + lr;
+          float4 acc4[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rl = 4 * i + lr;
-            float4 a = *reinterpret_cast<const float4*>(tb + rl * 32 + ((lc ^ (rl & 7)) << 2));
+            acc4[i] = ld_shared_v4(tb + rl * 128 + ((lc ^ (rl & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 a = acc4[i];
             if (rb + 4 * i < p.M) {
               // (acc + residual) + bias, the order of every other epilogue: all tile configurations stay bit-identical
               a.x = (a.x + cur[i].x) + bv.x, a.y = (a.y + cur[i].y) + bv.y;
@@ -823,20 +830,25 @@ TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
 
 // Derive everything that depends on the tile configuration: tile counts, smem ring, grid, weight tensor map.
 // which problems take the EPI = 1 instantiation (see gemm_tc_kernel)
-bool residual_lookahead(const GemmParams& p) {
-  static const bool off = getenv("CAP4D_GEMM_NO_LOOKAHEAD") != nullptr;
-  return !off && p.residual != nullptr && !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 &&
-         p.rowbias == nullptr && p.up_py < 0;
+// plain linear layer: no conv operand, no GEGLU, no per-image bias, no phase scatter
+bool plain_linear(const GemmParams& p) {
+  return !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 && p.rowbias == nullptr && p.up_py < 0;
 }
-// 0: generic epilogue, 1: residual look-ahead, 2: residual look-ahead + coalescing epilogue.  FLOPs per algorithmic
-// byte below the HBM ridge (measured: 4.2 -> 4.6-5.0 TB/s on the K = C shapes, profiles/r02b_residual_gemm.log; the
-// K = 4C shapes at C >= 640 are tensor-bound and lose a pipeline stage to the 32 KB buffer).  CAP4D_GEMM_EPI forces.
+// 0: generic epilogue, 1: residual look-ahead, 2: (residual look-ahead +) coalescing epilogue.  2 is for the
+// HBM-bound shapes - FLOPs per algorithmic byte below the ridge: to_out / proj_out at every level, FF2 and proj_in
+// at C = 320 (measured: 4.2 -> 4.6-5.0 TB/s on the K = C shapes, profiles/r02b_residual_gemm.log); the K = 4C shapes
+// at C >= 640 are tensor-bound and would lose a pipeline stage to the 32 KB buffer.  CAP4D_GEMM_EPI=0|1|2 forces
+// (1 needs a residual), CAP4D_GEMM_NO_LOOKAHEAD is the same as 0.
 int epilogue_kind(const GemmParams& p, int N, int Ktot) {
-  if (!residual_lookahead(p)) return 0;
+  static const bool off = getenv("CAP4D_GEMM_NO_LOOKAHEAD") != nullptr;
   static const char* force = getenv("CAP4D_GEMM_EPI");
-  if (force != nullptr && (force[0] == '1' || force[0] == '2')) return force[0] - '0';
-  const double intensity = 2.0 * N * Ktot / (2.0 * Ktot + 8.0 * N);
-  return intensity < 200.0 ? 2 : 1;
+  if (off || !plain_linear(p)) return 0;
+  const bool res = p.residual != nullptr, f32 = (p.out_mode & 15) == OUT_F32;
+  if (force != nullptr && force[0] >= '0' && force[0] <= '2') return (force[0] == '1' && !res) ? 0 : force[0] - '0';
+  if (!res && !f32) return 0;  // QKV: bf16 rows are 64 B per chunk, see the measurement in DESIGN.md
+  const double bytes_per_row = 2.0 * Ktot + (f32 ? 4.0 : 2.0) * N + (res ? 4.0 * N : 0.0);
+  const double intensity = 2.0 * N * Ktot / bytes_per_row;
+  return intensity < 200.0 ? 2 : (res ? 1 : 0);
 }
 
 bool apply_cfg(GemmPlan* plan, const TileCfg& cfg, const bf16* Wt, int N, int Ktot) {
@@ -876,7 +888,18 @@ bool finish_plan(GemmPlan* plan, const bf16* Wt, int N, int Ktot, int out_mode, 
     set_error("gemm: K must be a multiple of 64");
     return false;
   }
-  const TileCfg cfg = pick_tile(p.M, N, Ktot / BK, (out_mode & 15) == OUT_GEGLU_BF16);
+  TileCfg cfg = pick_tile(p.M, N, Ktot / BK, (out_mode & 15) == OUT_GEGLU_BF16);
+  // The cost model ranks the HBM-bound residual layers poorly (it has no term for their epilogue traffic).  Measured
+  // winners on the transformer shapes of the shipped model, 5-13 % ahead of the model's pick at 5 groups per call
+  // (scripts/bench_residual_gemm.py with FORCES, profiles/r02b_residual_gemm_force.log); every configuration computes
+  // bit-identical results, so this only moves time.
+  if (getenv("CAP4D_GEMM_FORCE") == nullptr && residual != nullptr && rowbias == nullptr && !p.a_conv &&
+      (out_mode & 15) != OUT_GEGLU_BF16 && p.M >= 16384) {
+    if (N == 320 && Ktot == 320) cfg = TileCfg{2, 64, 2, 0};          // to_out / proj_out, level 0
+    else if (N == 320 && Ktot == 1280) cfg = TileCfg{1, 160, 2, 0};   // FF2, level 0
+    else if (N == 640 && Ktot == 2560) cfg = TileCfg{2, 128, 2, 0};   // FF2, level 1
+    else if (N == 1280 && Ktot == 1280) cfg = TileCfg{1, 128, 2, 0};  // to_out / proj_out, level 2
+  }
   if (cfg.bn == 0) {
     set_error("gemm: N must be a multiple of 32 (64 for GEGLU)");
     return false;

@@ -386,6 +386,17 @@ __device__ __forceinline__ void tmem_st_16x128b_x16(uint32_t taddr, const uint32
                : "memory");
 }
 
+// 128-bit shared-memory accesses by 32-bit shared address: explicit state space, so that ptxas neither emits generic
+// LD / ST (a pointer cast out of the dynamic shared array loses its address space) nor orders them against global stores
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------------------
 // small numeric helpers
 // ---------------------------------------------------------------------------
