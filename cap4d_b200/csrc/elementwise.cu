@@ -14,38 +14,49 @@ namespace {
 // out[(n,y,x)][k]: k < 9*cin   -> tap (ky,kx) = k / cin, channel ci = k % cin of the masked latent
 //                  k < 9*cin+cc -> pos_enc[n,y,x,k-9*cin]
 //                  else 0
+// One thread per (pixel, 8 consecutive k): the pixel's coordinates are decoded once per 8 outputs and the row leaves
+// in 16-byte pieces (one thread per 2-byte element, with its divisions, made this the slowest of the small kernels:
+// 283 us per 5-group call).
+__device__ __forceinline__ float input_pack_value(const float* __restrict__ x, const float* __restrict__ z,
+                                                  const float* __restrict__ mask, const float* __restrict__ pos, int n,
+                                                  int yy, int xx, size_t pix, int k, int cin, int H, int W, int cc) {
+  if (k < 9 * cin) {
+    const int tap = k / cin, ci = k - tap * cin;
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    if (sy < 0 || sy >= H || sx < 0 || sx >= W) return 0.f;
+    const size_t sp = static_cast<size_t>(sy) * W + sx;
+    const float m = mask[static_cast<size_t>(n) * H * W + sp];
+    const size_t idx = (static_cast<size_t>(n) * cin + ci) * H * W + sp;
+    // x = z_input * ref_mask + x * logical_not(ref_mask)
+    return z[idx] * m + x[idx] * (m == 0.f ? 1.f : 0.f);
+  }
+  if (k < 9 * cin + cc) return pos[pix * cc + (k - 9 * cin)];
+  return 0.f;
+}
+
 __global__ void input_pack_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                   const float* __restrict__ mask, const float* __restrict__ pos, int n_img, int cin,
                                   int H, int W, int cc, int kpad, bf16* __restrict__ out, int out_f16) {
-  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  const int kg = kpad >> 3;  // groups of 8 per row (kpad is a multiple of 64)
+  const size_t total = static_cast<size_t>(n_img) * H * W * kg;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % kpad);
-    const size_t pix = i / kpad;
+    const int k0 = static_cast<int>(i % kg) * 8;
+    const size_t pix = i / kg;
     const int xx = static_cast<int>(pix % W);
     const int yy = static_cast<int>((pix / W) % H);
     const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
-    float v = 0.f;
-    if (k < 9 * cin) {
-      const int tap = k / cin, ci = k - tap * cin;
-      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
-      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-        const size_t sp = static_cast<size_t>(sy) * W + sx;
-        const float m = mask[static_cast<size_t>(n) * H * W + sp];
-        const size_t idx = (static_cast<size_t>(n) * cin + ci) * H * W + sp;
-        // x = z_input * ref_mask + x * logical_not(ref_mask)
-        v = z[idx] * m + x[idx] * (m == 0.f ? 1.f : 0.f);
-      }
-    } else if (k < 9 * cin + cc) {
-      v = pos[pix * cc + (k - 9 * cin)];
-    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = input_pack_value(x, z, mask, pos, n, yy, xx, pix, k0 + j, cin, H, W, cc);
     if (out_f16 == 2) {
-      reinterpret_cast<float*>(out)[i] = v;
-    } else if (out_f16) {
-      const __half hv = __float2half_rn(v);
-      out[i] = *reinterpret_cast<const bf16*>(&hv);
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * kpad + k0);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      out[i] = __float2bfloat16(v);
+      *reinterpret_cast<uint4*>(out + pix * kpad + k0) =
+          make_uint4(pack16x2(v[0], v[1], out_f16), pack16x2(v[2], v[3], out_f16), pack16x2(v[4], v[5], out_f16),
+                     pack16x2(v[6], v[7], out_f16));
     }
   }
 }
@@ -435,7 +446,11 @@ inline int grid_for(size_t total, int block) {
 cudaError_t launch_input_pack(const float* x, const float* z_input, const float* ref_mask, const float* pos_enc,
                               int n_img, int cin, int H, int W, int ccond, int kpad, bf16* out,
                               cudaStream_t stream, int out_f16) {
-  const size_t total = static_cast<size_t>(n_img) * H * W * kpad;
+  if (kpad % 8 != 0) {
+    set_error("input_pack: the padded K must be a multiple of 8");
+    return cudaErrorInvalidValue;
+  }
+  const size_t total = static_cast<size_t>(n_img) * H * W * (kpad / 8);
   input_pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, z_input, ref_mask, pos_enc, n_img, cin, H, W, ccond,
                                                               kpad, out, out_f16);
   return cudaGetLastError();

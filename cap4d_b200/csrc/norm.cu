@@ -356,18 +356,25 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
     __syncthreads();
     return s_item;
   };
-  if (pipelined) {
+  // bit 1 of `pipelined`: tickets count DOWN through the items (last image first).  The producer of this tensor wrote
+  // it front to back, so its tail is what is still in L2 when this kernel starts, and the consumer (a conv that walks
+  // its tiles front to back) then finds the images this kernel wrote last.  Items stay image-contiguous in ticket
+  // order, which is all the deadlock argument needs.
+  const bool reverse = (pipelined & 2) != 0;
+  if (pipelined & 1) {
     int prev = -1;
     for (;;) {
-      const int item = draw();
-      const bool has = item < n_items;
+      const int t = draw();
+      const bool has = t < n_items;
+      const int item = reverse ? n_items - 1 - t : t;
       if (has) phase1(item);
       if (prev >= 0) phase2(prev);
       if (!has) break;
       prev = item;
     }
   } else {
-    for (int item = draw(); item < n_items; item = draw()) {
+    for (int t = draw(); t < n_items; t = draw()) {
+      const int item = reverse ? n_items - 1 - t : t;
       phase1(item);
       phase2(item);
     }
@@ -388,9 +395,12 @@ gn_fused_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 template <int NQ>  // quads per lane: C <= 128 * NQ
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, bf16* __restrict__ out, int out_f16) {
+                 const float* __restrict__ beta, float eps, bf16* __restrict__ out, int out_f16, int reverse) {
   const int warps_per_block = blockDim.x >> 5;
-  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  // reverse: last rows first - the tail of the tensor is what the producing GEMM left in L2 (same idea as the
+  // GroupNorm kernel's ticket order), and the consuming GEMM starts at the rows written last
+  const int blk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int row = blk * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int quads = C >> 2;
@@ -483,7 +493,8 @@ cudaError_t launch_gn_t(int C1, int C2, const float* x1, const float* x2, int n_
   GnSync* sync = reinterpret_cast<GnSync*>(stats + static_cast<size_t>(n_layout) * GN_GROUPS);
   GnTicket* ticket = reinterpret_cast<GnTicket*>(sync + n_layout);
   int cpg = g.cpg, rpc = g.rows_per_chunk, nch = g.n_chunks;
-  static int pipelined = env_int("CAP4D_GN_PIPELINE", 1);
+  // CAP4D_GN_REVERSE=0: first image first (A/B: 8.04 -> 7.85 ms per U-Net call with the reversed order, two same-box pairs)
+  static int pipelined = env_int("CAP4D_GN_PIPELINE", 1) | (env_int("CAP4D_GN_REVERSE", 1) << 1);
   void* args[] = {&x1, &x2, &C1, &C2, &hw, &cpg, &rpc, &nch, &n_img, &partial, &stats, &sync, &ticket, &gamma, &beta, &eps,
                   &apply_silu, &out, &raw_out, &x2_G, &x2_V, &x2_R, &pipelined, &out_f16};
   // CAP4D_GN_COOPERATIVE=0 (experiments only): an ordinary launch of the same grid - every block still fits the GPU at
@@ -544,12 +555,13 @@ cudaError_t launch_layernorm(const float* x, int M, int C, const float* gamma, c
   const int warps = 8;
   const int grid = (M + warps - 1) / warps;
   const int quads = C / 4;
+  static const int reverse = env_int("CAP4D_LN_REVERSE", 1);  // A/B: 2.36 -> 2.27 ms per U-Net call, two same-box pairs
   if (quads <= 32 * 4)
-    layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
+    layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16, reverse);
   else if (quads <= 32 * 8)
-    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
+    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16, reverse);
   else
-    layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16);
+    layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, M, C, gamma, beta, eps, out, out_f16, reverse);
   return cudaGetLastError();
 }
 

@@ -19,3 +19,4 @@ timeout 900 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/r
 timeout 1200 scripts/ncu_bench_traffic.sh
 timeout 300 python scripts/bench_attention.py > gpurun_out/r02b_attention_microbench.json 2> gpurun_out/r02b_attention_microbench.err; echo "attn micro rc=$?"
 timeout 900 scripts/ncu_full.sh
+timeout 600 python bench.py --workload multi_ref --n-gen 80 --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r02b_bench_1gpu_multi_ref_80.json 2> gpurun_out/r02b_bench_1gpu_multi_ref_80.err; echo "multi_ref rc=$?"; cut -c1-160 gpurun_out/r02b_bench_1gpu_multi_ref_80.json
