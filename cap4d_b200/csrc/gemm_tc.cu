@@ -99,6 +99,15 @@ __device__ __forceinline__ void load_vec32(float (&dst)[32], const float* __rest
   for (int j = 0; j < 32; j += 8) ld_global_nc_v8(src + j, dst + j);
 }
 
+// acc[0..31] += 32 consecutive floats at shared address `addr` (every lane reads the same words: broadcast)
+__device__ __forceinline__ void add_vec32_shared(float* acc, uint32_t addr) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = ld_shared_v4(addr + j * 4);
+    acc[j] += t.x, acc[j + 1] += t.y, acc[j + 2] += t.z, acc[j + 3] += t.w;
+  }
+}
+
 __device__ __forceinline__ void add_vec32(float* acc, const float* __restrict__ src) {
   float b[32];
 #pragma unroll
@@ -416,6 +425,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (cc + 1 < c_end) process(cc + 1, r1, r0);
         }
       } else {
+      // The tile's BN bias values are the same for every row.  Read from global memory inside the chunk loop they
+      // were the top stall of the GEGLU GEMM (ncu: 37 % of all warp samples waiting on the bias adds); each epilogue
+      // warp keeps its own copy of the slice in shared memory instead - no block-wide barrier (the staged version of
+      // round 1 needed one and lost) - and requests the NEXT tile's slice before it starts on this tile's chunks.
+      const bool bias_smem = p.bias_smem != 0 && p.bias != nullptr;
+      const uint32_t wb = smem_u32(epi_buf) + (warp - EPI_WARP0) * 1024;  // 256 floats per warp
+      float4 nb0 = make_float4(0.f, 0.f, 0.f, 0.f), nb1 = nb0;
+      auto bias_request = [&](int n_t) {
+        const float* bsrc = p.bias + n_t * p.BN;
+        if (lane * 4 < p.BN) nb0 = __ldg(reinterpret_cast<const float4*>(bsrc + lane * 4));
+        if (lane * 4 + 128 < p.BN) nb1 = __ldg(reinterpret_cast<const float4*>(bsrc + lane * 4 + 128));
+      };
+      auto bias_publish = [&]() {
+        __syncwarp();  // every lane is done reading the previous slice
+        st_shared_v4(wb + lane * 16, __float_as_uint(nb0.x), __float_as_uint(nb0.y), __float_as_uint(nb0.z), __float_as_uint(nb0.w));
+        st_shared_v4(wb + 512 + lane * 16, __float_as_uint(nb1.x), __float_as_uint(nb1.y), __float_as_uint(nb1.z), __float_as_uint(nb1.w));
+        __syncwarp();
+      };
+      if (bias_smem) {
+        if (it == 0) {
+          bias_request(n_tile);
+          bias_publish();
+        }
+        const int next = tile + static_cast<int>(gridDim.x);
+        if (next < total_tiles) bias_request(next - (next / p.tiles_n) * p.tiles_n);
+      }
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint32_t v[32], vg[32];
@@ -443,7 +478,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (row_ok) {
             const int col0 = n_tile * p.BN + c * 64;
-            if (p.bias != nullptr) {
+            if (bias_smem) {
+              add_vec32_shared(a, wb + c * 256);
+              add_vec32_shared(ag, wb + c * 256 + 128);
+            } else if (p.bias != nullptr) {
               add_vec32(a, p.bias + col0);
               add_vec32(ag, p.bias + col0 + 32);
             }
@@ -458,7 +496,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.residual != nullptr) add_vec32(a, p.residual + static_cast<size_t>(row) * p.ldr + col0);
             if (p.rowbias != nullptr)
               add_vec32(a, p.rowbias + static_cast<size_t>(row / p.rowbias_div) * p.rowbias_ld + col0);
-            if (p.bias != nullptr) add_vec32(a, p.bias + col0);
+            if (bias_smem) add_vec32_shared(a, wb + c * 128);
+            else if (p.bias != nullptr) add_vec32(a, p.bias + col0);
             if ((p.out_mode & 15) == OUT_F32) {
               epilogue_store_f32(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0, a);
             } else {
@@ -467,6 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (bias_smem && tile + static_cast<int>(gridDim.x) < total_tiles) bias_publish();
       }  // generic epilogue
       tc_fence_before();
       mbar_arrive(&tail->tmem_empty[acc]);
@@ -830,6 +870,11 @@ TileCfg pick_tile(int M, int N, int num_kb, bool geglu) {
 
 // Derive everything that depends on the tile configuration: tile counts, smem ring, grid, weight tensor map.
 // which problems take the EPI = 1 instantiation (see gemm_tc_kernel)
+int env_int_or(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
 // plain linear layer: no conv operand, no GEGLU, no per-image bias, no phase scatter
 bool plain_linear(const GemmParams& p) {
   return !p.a_conv && (p.out_mode & 15) != OUT_GEGLU_BF16 && (p.out_mode & 32) == 0 && p.rowbias == nullptr && p.up_py < 0;
@@ -865,7 +910,12 @@ bool apply_cfg(GemmPlan* plan, const TileCfg& cfg, const bf16* Wt, int N, int Kt
   p.num_kb = Ktot / BK;
   const int stage_bytes = cfg.two_cta ? (A_SUB_BYTES + (bn / 2) * BK * 2) : (cfg.msub * A_SUB_BYTES + bn * BK * 2);
   p.epi = cfg.two_cta ? 0 : epilogue_kind(p, N, Ktot);
-  const int epi_extra = p.epi == 2 ? EPI_BUF_OFFSET + EPI_BUF_BYTES : 0;
+  // generic epilogue: per-warp bias slices in shared memory (CAP4D_GEMM_BIAS_SMEM: 0 off, 1 GEGLU only, 2 every bias)
+  static const int bias_mode = env_int_or("CAP4D_GEMM_BIAS_SMEM", 2);
+  const bool is_geglu = (p.out_mode & 15) == OUT_GEGLU_BF16;
+  p.bias_smem = (!cfg.two_cta && p.epi == 0 && p.bias != nullptr && (p.out_mode & 32) == 0 &&
+                 (bias_mode == 2 || (bias_mode == 1 && is_geglu))) ? 1 : 0;
+  const int epi_extra = p.epi == 2 ? EPI_BUF_OFFSET + EPI_BUF_BYTES : (p.bias_smem ? EPI_BUF_OFFSET + 8 * 1024 : 0);
   int stages = (220 * 1024 - static_cast<int>(sizeof(SmemTail)) - 1024 - epi_extra) / stage_bytes;
   stages = std::min(stages, MAX_STAGES);
   stages = std::min(stages, std::max(2, p.num_kb));

@@ -34,6 +34,7 @@ struct GemmParams {
   int msub;          // 128-row sub-tiles per CTA tile (1 or 2)
   int n_acc;         // TMEM accumulator stages (2 if msub*BN <= 256)
   int epi;           // epilogue instantiation (gemm_tc.cu, epilogue_kind): 0 generic, 1 residual look-ahead, 2 + coalescing
+  int bias_smem;     // generic epilogue: each warp keeps the tile's bias slice in shared memory
   int tiles_m, tiles_n;
   int num_kb;        // K / 64 over all segments
   int seg0_kb;       // k-blocks served by A (taps * cin_kb for conv); the rest come from A2

@@ -20,3 +20,11 @@ timeout 1200 scripts/ncu_bench_traffic.sh
 timeout 300 python scripts/bench_attention.py > gpurun_out/r02b_attention_microbench.json 2> gpurun_out/r02b_attention_microbench.err; echo "attn micro rc=$?"
 timeout 900 scripts/ncu_full.sh
 timeout 600 python bench.py --workload multi_ref --n-gen 80 --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r02b_bench_1gpu_multi_ref_80.json 2> gpurun_out/r02b_bench_1gpu_multi_ref_80.err; echo "multi_ref rc=$?"; cut -c1-160 gpurun_out/r02b_bench_1gpu_multi_ref_80.json
+CAP4D_GEMM_BIAS_SMEM=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r02b_bench_bias_global.json 2>/dev/null; echo "bias-from-global A/B rc=$?"
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r02b_bench_bias_smem.json 2>/dev/null
+python - <<'PY'
+import json
+for n in ("bias_global", "bias_smem"):
+    d = json.loads([l for l in open(f"gpurun_out/r02b_bench_{n}.json") if l.startswith("{")][-1])
+    print(n, round(d["value"], 4), round(d["unet_step_ms"], 2), d["clocks"]["sm_mhz"], {k: round(v["ms_per_call"], 2) for k, v in d["kernels"].items()})
+PY

@@ -14,4 +14,5 @@ cap conv gemm_tc_kernel python scripts/one_conv.py 80 64 64 320 320 3
 cap gn gn_fused_kernel python scripts/one_gn.py 80 4096 320 0 3
 cap attn attn_tc_kernel python scripts/one_attn.py 4096 320 80 3
 cap lin gemm_tc_kernel python scripts/one_gemm.py 327680 320 320 0 1 3
+cap geglu gemm_tc_kernel python scripts/one_gemm.py 327680 2560 320 2 0 3
 ls -la gpurun_out/r02_full_*.ncu-rep
